@@ -1,0 +1,111 @@
+/* libpgpfa_b200 — C ABI of the B200-native Poisson-GPFA EM hot path.
+ *
+ * The reference (mackelab/poisson-gpfa) has no FFI: its boundary is the Python module API
+ * (funs/engine.py, funs/inference.py, funs/learning.py, funs/util.py).  This header declares the
+ * entry points a ctypes binding of that API needs; each one cites the reference code it replaces.
+ * The Python mirror lives in poisson_gpfa_b200/{util,inference,learning,engine}.py and calls ONLY
+ * these functions for arithmetic (no CPU fallback).
+ *
+ * Conventions: every array pointer is a DEVICE pointer (float64 unless stated, C-contiguous);
+ * scalars by value; `stream` is a cudaStream_t passed as void*-compatible handle; every function
+ * returns 0 on success or a PGPFA_ERR_* code and never throws.  The library owns no device memory:
+ * callers pass workspaces sized by the *_workspace_bytes helpers.  One handle per device/thread.
+ *
+ * Layouts: x[r][k][t] (latent-major, funs/inference.py:97 reshape), y[r][n][t], C[n][k], d[n],
+ * K / Kinv [k][s][t], W[r][k*q+l][t], post_vsm[r][t][k][l] (= reference post_vsm[r], (T,q,q)),
+ * post_vsmGP[r][k][s][t] (reference post_vsmGP[r] is (T,T,q): transpose of this), theta[n][q+1]=[C|d].
+ * Factor tiles: 64x64 fragment-major tiles, packed lower (L) / packed upper (ZT = L^-T), see DESIGN.md.
+ */
+#ifndef PGPFA_B200_H
+#define PGPFA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+typedef struct pgpfa_handle_s *pgpfa_handle_t;
+
+#define PGPFA_ABI_VERSION 1
+
+/* ---- lifecycle / errors -------------------------------------------------------------------- */
+int pgpfa_abi_version(void);
+int pgpfa_create(pgpfa_handle_t *out);                 /* fails with PGPFA_ERR_NO_DEVICE without a GPU */
+int pgpfa_destroy(pgpfa_handle_t h);
+const char *pgpfa_error_string(int code);
+const char *pgpfa_last_cuda_error(void);
+
+/* ---- (1) GP prior: funs/util.py:599-619 makeK_big, funs/inference.py:82 inv(K_big) ---------- */
+int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double epsNoise, double *K, cudaStream_t stream);
+int pgpfa_make_K_big(const double *K, int q, int T, double *K_big, cudaStream_t stream);
+/* K(p), dK/dgamma for the timescale M-step, gamma = exp(p) in bins^-2: funs/learning.py:183-185 */
+int pgpfa_make_K_gamma(const double *p, int q, int T, double epsNoise, double *K, double *dK, cudaStream_t stream);
+/* batched SPD inverse + logdet through the tiled Cholesky (np.linalg.inv / slogdet replacement) */
+long long pgpfa_spd_inverse_workspace_bytes(int batch, int n);
+int pgpfa_spd_inverse_batched(const double *A, int batch, int n, double *Ainv, double *logdet, int *info,
+                              void *workspace, long long ws_bytes, cudaStream_t stream);
+
+/* ---- factorisation primitives (exposed for tests and roofline micro-benchmarks) -------------- */
+long long pgpfa_tiles_bytes(int n);        /* bytes of one packed-triangular tile set (L or ZT) */
+long long pgpfa_dinv_bytes(int n);         /* bytes of one set of inverted diagonal tiles */
+int pgpfa_potrf_dense(const double *A, int batch, int n, double *L_tiles, double *Dinv_tiles, double *ZT_tiles_or_null,
+                      int *info, cudaStream_t stream);
+/* factor H = blkdiag(Kinv_k) + scatter(W) (* diag_scale on the diagonal) without materialising it:
+ * funs/inference.py:50-65 negLogPosteriorUnNorm_hess, :188-190 VIPostCov */
+int pgpfa_potrf_posterior(const double *Kinv, const double *W, double diag_scale, int batch, int q, int T,
+                          double *L_tiles, double *Dinv_tiles, double *ZT_tiles_or_null, int *info,
+                          cudaStream_t stream);
+int pgpfa_potrs(const double *L_tiles, const double *Dinv_tiles, const double *rhs, double scale, int batch, int n,
+                double *out, cudaStream_t stream);
+int pgpfa_trtri(const double *L_tiles, const double *Dinv_tiles, double *ZT_tiles, int batch, int n, cudaStream_t stream);
+int pgpfa_potri_dense(const double *ZT_tiles, int batch, int n, double *Ainv, void *workspace, long long ws_bytes,
+                      cudaStream_t stream);
+int pgpfa_cov_slices(const double *ZT_tiles, int batch, int q, int T, double *vsm, double *vsmGP, void *workspace,
+                     long long ws_bytes, cudaStream_t stream);
+int pgpfa_logdet(const double *L_tiles, int batch, int n, double *logdet, cudaStream_t stream);
+int pgpfa_tiles_to_dense(const double *tiles, int batch, int n, int upper, double *out, cudaStream_t stream);
+
+/* ---- (2) Laplace E-step: funs/inference.py:12-185 -------------------------------------------- */
+int pgpfa_prior_apply(const double *Kmat, const double *v, int R, int q, int T, double *out, cudaStream_t stream);
+/* f[r], g[r][k][t], W[r][kl][t] at given x; Kx_ws is an R*q*T scratch (receives Kinv x) */
+int pgpfa_laplace_eval(const double *x, const double *y, const double *C, const double *d, const double *Kinv, int R,
+                       int q, int N, int T, double *f, double *g, double *W, double *Kx_ws, cudaStream_t stream);
+int pgpfa_hessian_dense(const double *Kinv, const double *W, double diag_scale, int R, int q, int T, double *H,
+                        cudaStream_t stream);
+long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chunk);
+/* Batched Newton to ||step||_inf <= tol (1+||x||_inf) per trial, then posterior slices at the mode.
+ * x: in = start (zeros or warm start, funs/inference.py:99-102), out = mode (post_mean).
+ * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[4] = {trial-factorisations, max Newton
+ * iterations, trials not converged, chunk size}. */
+int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
+                        double *x, int R, int q, int N, int T, double tol, int max_newton, double *f_out, double *vsm,
+                        double *vsmGP, double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
+                        int *stats_out, cudaStream_t stream);
+
+/* ---- (4) M-step: funs/learning.py:20-309 (+ prior variants :445-534, :681-769) ---------------- */
+/* PautoSum[k][s][t] (+)= sum_r vsmGP[r][k][s][t] + m[r][k][s] m[r][k][t]   funs/learning.py:162-165 */
+int pgpfa_pautosum(const double *vsmGP, const double *post_mean, int R, int q, int T, int accumulate, double *P,
+                   cudaStream_t stream);
+int pgpfa_mstep_cd_nstats(int q);          /* 1 + (q+1) + (q+1)(q+2)/2 */
+long long pgpfa_mstep_cd_workspace_bytes(int q, int N);
+/* per-neuron un-normalised sums over local trials/bins of cost, gradient, Hessian of
+ * MStepObservationCost at theta: stats[s][n] */
+int pgpfa_mstep_cd_stats(const double *y, const double *post_mean, const double *vsm, const double *theta, int R, int q,
+                         int N, int T, double *stats, void *workspace, long long ws_bytes, cudaStream_t stream);
+/* one accept/reject + Newton-step update per neuron; see poisson_gpfa_b200/learning.py */
+int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *theta0, double *theta_cur,
+                          double *theta_try, double *fcur, double *step, double *alpha, double *slope, int *done,
+                          int first, double tol, int N, int q, int *n_open, cudaStream_t stream);
+long long pgpfa_tau_eval_workspace_bytes(int q, int T);
+/* cost[k], grad[k] of MStepGPtimescaleCost(+WithPrior) at p[k]; prior_w = 1/step^2 or 0 */
+int pgpfa_tau_eval(const double *p, const double *PautoSum, double numTrials, int q, int T, double epsNoise,
+                   double prior_w, const double *tau_old_sec, double binSize_ms, double *cost, double *grad,
+                   void *workspace, long long ws_bytes, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

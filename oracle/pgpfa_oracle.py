@@ -193,13 +193,16 @@ def newton_mode_struct(y, C, d, Kinv, x0=None, tol=1e-13, maxit=100):
             xn = x + a * step
             with np.errstate(over='ignore'):
                 fn = nlp_struct(xn, y, C, d, Kinv)
-            if np.isfinite(fn) and fn <= f + 1e-4 * a * slope:
+            # near the optimum the decrease is below the rounding noise of f: accept the full step
+            if abs(slope) <= 1e-9 * (1.0 + abs(f)):
+                break
+            if np.isfinite(fn) and fn <= f + 1e-4 * a * slope + 1e-13 * (1.0 + abs(f)):
                 break
             a *= 0.5
             if a < 1e-10:
                 break
         x, f = xn, fn
-        if np.abs(a * step).max() <= tol * (1.0 + np.abs(x).max()):
+        if a == 1.0 and np.abs(step).max() <= tol * (1.0 + np.abs(x).max()):
             break
     return x, f, it
 

@@ -1,0 +1,517 @@
+// Batched blocked FP64 Cholesky / triangular inverse / selected inverse of the qT x qT posterior
+// systems on the FP64 tensor pipe (DMMA.8x8x4), tiles staged through shared memory by bulk async
+// copies (UBLKCP).  Replaces the dense LAPACK calls of the reference:
+//   np.linalg.inv(hess)            funs/inference.py:130-131   (posterior covariance)
+//   Newton-CG's inner solves        funs/inference.py:119-126   (Newton step H d = -g)
+//   np.linalg.inv / slogdet         funs/inference.py:82,190,207; funs/learning.py:191-192
+// Algorithm (left-looking by block column j, 64x64 tiles, packed lower storage):
+//   diag kernel : S = A(j,j) - sum_k L(j,k) L(j,k)^T ; L(j,j) = chol(S) ; Dinv_j = L(j,j)^-1
+//   panel kernel: L(i,j) = (A(i,j) - sum_k L(i,k) L(j,k)^T) Dinv_j^T         for all i > j
+// Triangular inverse ZT = L^-T (packed upper, by block row i of L):
+//   ZT(j,i) = -(sum_{k=j}^{i-1} ZT(j,k) L(i,k)^T) Dinv_i^T                   for all j < i
+// Selected inverse Sigma = ZT ZT^T: only the tiles that are consumed (diagonal T x T blocks for
+// post_vsmGP, or everything for post_cov / K^-1); the time-diagonals (post_vsm) come from row Gram
+// products of ZT.
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Matrix element source: either generated on the fly  H = blkdiag(Kinv_k) + scatter(W)  (never
+// materialised) or read from a dense row-major batch.
+// ---------------------------------------------------------------------------------------------
+struct MatSource {
+    const double *Kinv;   // (q,T,T) or nullptr
+    const double *W;      // (trials, q*q, T)
+    const double *dense;  // (slots, n, n) when Kinv == nullptr
+    int q, T, n;
+    double diag_scale;    // 1 (Laplace) or 1+1e-6 (variational, funs/inference.py:190)
+};
+
+struct FragIdx {
+    int row[4], col[4];        // global matrix rows / first col of each pair
+    int rk[4], rs[4];          // latent / bin of each row      (-1 latent => padding)
+    int cl[4][2], ct[4][2];    // latent / bin of each column
+};
+
+__device__ __forceinline__ void frag_index(FragIdx &f, const MatSource &src, int ti, int tj, int wm, int wn, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = ti * PGPFA_NB + frag_row(wm, i, lane);
+        f.row[i] = r;
+        if (r < src.n) { f.rk[i] = r / src.T; f.rs[i] = r - f.rk[i] * src.T; } else { f.rk[i] = -1; f.rs[i] = 0; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c0 = tj * PGPFA_NB + frag_col(wn, j, lane);
+        f.col[j] = c0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c = c0 + e;
+            if (c < src.n) { f.cl[j][e] = c / src.T; f.ct[j][e] = c - f.cl[j][e] * src.T; } else { f.cl[j][e] = -1; f.ct[j][e] = 0; }
+        }
+    }
+}
+
+__device__ __forceinline__ double mat_elem(const MatSource &src, int trial, int slot, const FragIdx &f, int i, int j, int e) {
+    const int r = f.row[i], c = f.col[j] + e;
+    if (f.rk[i] < 0 || f.cl[j][e] < 0) return (r == c) ? 1.0 : 0.0;
+    double v;
+    if (src.Kinv == nullptr) {
+        v = src.dense[((size_t)slot * src.n + r) * src.n + c];
+    } else {
+        v = 0.0;
+        const int k = f.rk[i], s = f.rs[i], l = f.cl[j][e], t = f.ct[j][e];
+        if (k == l) v = __ldg(&src.Kinv[((size_t)k * src.T + s) * src.T + t]);
+        if (s == t) v += src.W[((size_t)trial * src.q * src.q + k * src.q + l) * src.T + t];
+    }
+    if (r == c) v *= src.diag_scale;
+    return v;
+}
+
+struct FactorArgs {
+    MatSource src;
+    double *L;          // slots x ltiles x 4096
+    double *Dinv;       // slots x nb x 4096
+    double *ZT;         // slots x ltiles x 4096 (packed upper) or nullptr
+    const int *act;     // slot -> trial, or nullptr (trial = slot)
+    int *info;          // per trial: 0 ok, >0 first non-positive pivot (1-based)
+    int nb;
+    int step;
+    int mode;           // panel kernel: 0 = Cholesky panel, 1 = triangular-inverse row
+};
+
+__device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal-tile kernel: SYRK update + 64x64 Cholesky + 64x64 triangular inverse (in shared memory)
+// ---------------------------------------------------------------------------------------------
+#define SLD 65
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_diag_kernel(FactorArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int slot = blockIdx.x;
+    const int trial = a.act ? a.act[slot] : slot;
+    const int j = a.step;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
+    double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
+
+    GemmPipe pipe;
+    pipe_setup(pipe, smem_raw);
+    double acc[4][4][2];
+    zero_acc(acc);
+    const double *Arow = Ls + ltile(j, 0) * PGPFA_TILE;
+    gemm_slabs<true>(acc, pipe, Arow, Arow, 2 * j);
+
+    double *S = reinterpret_cast<double *>(smem_raw);      // [64][65]
+    double *X = S + PGPFA_NB * SLD;                        // [64][65]
+    {
+        FragIdx f;
+        frag_index(f, a.src, j, j, wm, wn, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int r = frag_row(wm, i, lane), c = frag_col(wn, jj, lane) + e;
+                    if (c <= r) S[r * SLD + c] = mat_elem(a.src, trial, slot, f, i, jj, e) - acc[i][jj][e];
+                }
+    }
+    // right-looking unblocked Cholesky of the lower triangle of S
+    int bad = 0;
+    for (int c = 0; c < PGPFA_NB; c++) {
+        __syncthreads();
+        double piv = S[c * SLD + c];
+        if (!(piv > 0.0)) { if (!bad) bad = j * PGPFA_NB + c + 1; piv = 1.0; }
+        const double inv = 1.0 / piv;
+        const int m = PGPFA_NB - 1 - c;
+        for (int idx = tid; idx < m * m; idx += PGPFA_GEMM_THREADS) {
+            const int rr = idx / m, cc = idx - rr * m;
+            if (cc <= rr) {
+                const int r = c + 1 + rr, c2 = c + 1 + cc;
+                S[r * SLD + c2] -= S[r * SLD + c] * S[c2 * SLD + c] * inv;
+            }
+        }
+        __syncthreads();
+        const double d = sqrt(piv);
+        if (tid == 0) S[c * SLD + c] = d;
+        for (int r = c + 1 + tid; r < PGPFA_NB; r += PGPFA_GEMM_THREADS) S[r * SLD + c] = S[r * SLD + c] / d;
+    }
+    __syncthreads();
+    if (bad && tid == 0 && a.info) atomicCAS(&a.info[trial], 0, bad);
+    // X = L^-1 by column-parallel forward substitution (thread c owns column c)
+    if (tid < PGPFA_NB) {
+        const int c = tid;
+        for (int r = 0; r < PGPFA_NB; r++) {
+            double v;
+            if (r < c) v = 0.0;
+            else if (r == c) v = 1.0 / S[c * SLD + c];
+            else {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int k = c;
+                for (; k + 3 < r; k += 4) {
+                    s0 += S[r * SLD + k] * X[k * SLD + c];
+                    s1 += S[r * SLD + k + 1] * X[(k + 1) * SLD + c];
+                    s2 += S[r * SLD + k + 2] * X[(k + 2) * SLD + c];
+                    s3 += S[r * SLD + k + 3] * X[(k + 3) * SLD + c];
+                }
+                for (; k < r; k++) s0 += S[r * SLD + k] * X[k * SLD + c];
+                v = -((s0 + s1) + (s2 + s3)) / S[r * SLD + r];
+            }
+            X[r * SLD + c] = v;
+        }
+    }
+    __syncthreads();
+    double *Lt = Ls + ltile(j, j) * PGPFA_TILE;
+    double *Dt = a.Dinv + ((size_t)slot * a.nb + j) * PGPFA_TILE;
+    double *Zt = a.ZT ? a.ZT + ((size_t)slot * ltl + utile(j, j, a.nb)) * PGPFA_TILE : nullptr;
+    for (int off = tid; off < PGPFA_TILE; off += PGPFA_GEMM_THREADS) {
+        const int r = (((off >> 6) & 7) << 3) + ((off >> 3) & 7);
+        const int c = ((off >> 11) << 5) + (((off >> 9) & 3) << 3) + (off & 7);
+        Lt[off] = (c <= r) ? S[r * SLD + c] : 0.0;
+        Dt[off] = (c <= r) ? X[r * SLD + c] : 0.0;
+        if (Zt) Zt[off] = (r <= c) ? X[c * SLD + r] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel kernel: out = (init - sum_k A_k B_k^T) * D^T   (Cholesky panel tile or inverse-row tile)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(FactorArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int slot = blockIdx.y;
+    const int trial = a.act ? a.act[slot] : slot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
+    double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
+    double *Zs = a.ZT ? a.ZT + (size_t)slot * ltl * PGPFA_TILE : nullptr;
+
+    const double *A, *B, *D;
+    double *out;
+    int nslab, ti = 0, tj = 0;
+    if (a.mode == 0) {
+        const int j = a.step, i = j + 1 + blockIdx.x;
+        A = Ls + ltile(i, 0) * PGPFA_TILE;
+        B = Ls + ltile(j, 0) * PGPFA_TILE;
+        nslab = 2 * j;
+        D = a.Dinv + ((size_t)slot * a.nb + j) * PGPFA_TILE;
+        out = Ls + ltile(i, j) * PGPFA_TILE;
+        ti = i; tj = j;
+    } else {
+        const int i = a.step, j = blockIdx.x;
+        A = Zs + utile(j, j, a.nb) * PGPFA_TILE;
+        B = Ls + ltile(i, j) * PGPFA_TILE;
+        nslab = 2 * (i - j);
+        D = a.Dinv + ((size_t)slot * a.nb + i) * PGPFA_TILE;
+        out = Zs + utile(j, i, a.nb) * PGPFA_TILE;
+    }
+    GemmPipe pipe;
+    pipe_setup(pipe, smem_raw);
+    uint64_t *aux = pipe.full + PGPFA_STAGES;
+    if (tid == 0) { mbar_init(aux, 1); mbar_fence_init(); }
+    double acc[4][4][2];
+    zero_acc(acc);
+    gemm_slabs<false>(acc, pipe, A, B, nslab);
+    __syncthreads();
+    double *St = pipe.stages;                 // 32 KB: (init - acc) in operand layout
+    double *Dt = pipe.stages + PGPFA_TILE;    // 32 KB: Dinv tile
+    if (tid == 0) {
+        mbar_expect_tx(aux, PGPFA_TILE * 8);
+        bulk_g2s(Dt, D, PGPFA_TILE * 8, aux);
+    }
+    {
+        double2 *S2 = reinterpret_cast<double2 *>(St);
+        if (a.mode == 0) {
+            FragIdx f;
+            frag_index(f, a.src, ti, tj, wm, wn, lane);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double2 v;
+                    v.x = mat_elem(a.src, trial, slot, f, i, jj, 0) - acc[i][jj][0];
+                    v.y = mat_elem(a.src, trial, slot, f, i, jj, 1) - acc[i][jj][1];
+                    S2[frag_slot2(wm, wn, i, jj, lane)] = v;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double2 v;
+                    v.x = -acc[i][jj][0];
+                    v.y = -acc[i][jj][1];
+                    S2[frag_slot2(wm, wn, i, jj, lane)] = v;
+                }
+        }
+    }
+    __syncthreads();
+    mbar_wait(aux, 0);
+    zero_acc(acc);
+    slab_mma(acc, St, Dt, wm, wn, lane);
+    if (wn == 1) slab_mma(acc, St + PGPFA_SLAB, Dt + PGPFA_SLAB, wm, wn, lane);   // D lower-triangular: k<=n
+    double2 *O2 = reinterpret_cast<double2 *>(out);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            double2 v;
+            v.x = acc[i][jj][0];
+            v.y = acc[i][jj][1];
+            O2[frag_slot2(wm, wn, i, jj, lane)] = v;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Selected inverse tiles: Sigma(a,b) = sum_{m>=a} ZT(a,m) ZT(b,m)^T, scattered to the consumer layout
+// ---------------------------------------------------------------------------------------------
+struct LauumArgs {
+    const double *ZT;
+    const int2 *pairs;       // (a, b), a >= b
+    const int *act;          // slot -> trial (output index), or nullptr
+    double *vsmGP;           // (trials, q, T, T) or nullptr
+    double *dense;           // (slots, n, n) or nullptr
+    int nb, n, q, T;
+};
+
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) lauum_tiles_kernel(LauumArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int slot = blockIdx.y;
+    const int trial = a.act ? a.act[slot] : slot;
+    const int2 pr = a.pairs[blockIdx.x];
+    const int ta = pr.x, tb = pr.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
+    const double *Zs = a.ZT + (size_t)slot * ltl * PGPFA_TILE;
+    GemmPipe pipe;
+    pipe_setup(pipe, smem_raw);
+    double acc[4][4][2];
+    zero_acc(acc);
+    const double *A = Zs + utile(ta, ta, a.nb) * PGPFA_TILE;
+    const double *B = Zs + utile(tb, ta, a.nb) * PGPFA_TILE;
+    if (ta == tb) gemm_slabs<true>(acc, pipe, A, A, 2 * (a.nb - ta));
+    else gemm_slabs<false>(acc, pipe, A, B, 2 * (a.nb - ta));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = ta * PGPFA_NB + frag_row(wm, i, lane);
+        if (r >= a.n) continue;
+        const int rk = r / a.T, rs = r - rk * a.T;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = tb * PGPFA_NB + frag_col(wn, jj, lane) + e;
+                if (c >= a.n) continue;
+                const double v = acc[i][jj][e];
+                if (a.dense) {
+                    double *dd = a.dense + (size_t)slot * a.n * a.n;
+                    dd[(size_t)r * a.n + c] = v;
+                    dd[(size_t)c * a.n + r] = v;
+                }
+                if (a.vsmGP) {
+                    const int ck = c / a.T;
+                    if (ck == rk) {
+                        const int cs = c - ck * a.T;
+                        double *g = a.vsmGP + ((size_t)trial * a.q + rk) * a.T * a.T;
+                        g[(size_t)rs * a.T + cs] = v;
+                        g[(size_t)cs * a.T + rs] = v;
+                    }
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Time-diagonal blocks: vsm[t][k][l] = Sigma[kT+t, lT+t] = <row kT+t of ZT, row lT+t of ZT>
+// one warp per bin t; each lane streams 16-byte pieces of the q rows tile by tile
+// ---------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) cov_timediag_kernel(const double *__restrict__ ZT, const int *act,
+                                                           double *__restrict__ vsm, int nb, int T) {
+    const int slot = blockIdx.y;
+    const int trial = act ? act[slot] : slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + warp;
+    if (t >= T) return;
+    const long long ltl = (long long)nb * (nb + 1) / 2;
+    const double *Zs = ZT + (size_t)slot * ltl * PGPFA_TILE;
+    int arow[Q], roff[Q];
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int rho = k * T + t;
+        arow[k] = rho >> 6;
+        const int r = rho & 63;
+        roff[k] = ((r >> 3) << 6) + ((r & 7) << 3);
+    }
+    const int seg = lane >> 2;
+    const int loff = ((seg >> 2) << 11) + ((seg & 3) << 9) + 2 * (lane & 3);
+    double acc[Q * (Q + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < Q * (Q + 1) / 2; i++) acc[i] = 0.0;
+    for (int m = arow[0]; m < nb; m++) {
+        double2 v[Q];
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            if (m >= arow[k]) {
+                v[k] = *reinterpret_cast<const double2 *>(Zs + utile(arow[k], m, nb) * PGPFA_TILE + roff[k] + loff);
+            } else {
+                v[k].x = 0.0; v[k].y = 0.0;
+            }
+        }
+        int idx = 0;
+#pragma unroll
+        for (int k = 0; k < Q; k++)
+#pragma unroll
+            for (int l = k; l < Q; l++) { acc[idx] += v[k].x * v[l].x + v[k].y * v[l].y; idx++; }
+    }
+    double *o = vsm + ((size_t)trial * T + t) * Q * Q;
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < Q; k++)
+#pragma unroll
+        for (int l = k; l < Q; l++) {
+            const double s = warp_sum(acc[idx]);
+            idx++;
+            if (lane == 0) { o[k * Q + l] = s; o[l * Q + k] = s; }
+        }
+}
+
+// log-determinant from the diagonal of the factor: 2 * sum log L_ii  (per slot)
+__global__ void chol_logdet_kernel(const double *__restrict__ L, int nb, int n, double *__restrict__ out) {
+    __shared__ double red[32];
+    const int slot = blockIdx.x;
+    const long long ltl = (long long)nb * (nb + 1) / 2;
+    const double *Ls = L + (size_t)slot * ltl * PGPFA_TILE;
+    double s = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int j = r >> 6, rr = r & 63;
+        s += log(Ls[ltile(j, j) * PGPFA_TILE + tile_off(rr, rr)]);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[slot] = 2.0 * s;
+}
+
+// debug / test helper: packed-lower tiles -> dense row-major lower-triangular (n x n per slot)
+__global__ void tiles_to_dense_kernel(const double *__restrict__ L, int nb, int n, int upper, double *__restrict__ out) {
+    const int slot = blockIdx.y;
+    const long long ltl = (long long)nb * (nb + 1) / 2;
+    const double *Ls = L + (size_t)slot * ltl * PGPFA_TILE;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)n * n; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+        double v = 0.0;
+        if (!upper && c <= r) v = Ls[ltile(r >> 6, c >> 6) * PGPFA_TILE + tile_off(r & 63, c & 63)];
+        if (upper && r <= c) v = Ls[utile(r >> 6, c >> 6, nb) * PGPFA_TILE + tile_off(r & 63, c & 63)];
+        out[(size_t)slot * n * n + e] = v;
+    }
+}
+
+int set_smem_attrs() {
+    static bool done = false;
+    if (done) return PGPFA_OK;
+    PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGPFA_GEMM_SMEM));
+    PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGPFA_GEMM_SMEM));
+    PGPFA_CUDA_TRY(cudaFuncSetAttribute(lauum_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGPFA_GEMM_SMEM));
+    done = true;
+    return PGPFA_OK;
+}
+
+template <int Q>
+void launch_timediag(const double *ZT, const int *act, double *vsm, int nb, int T, int nslots, cudaStream_t st) {
+    dim3 grid((T + 3) / 4, nslots);
+    cov_timediag_kernel<Q><<<grid, 128, 0, st>>>(ZT, act, vsm, nb, T);
+}
+
+}  // namespace
+
+// =============================================================================================
+// internal host API (used by laplace.cu / mstep.cu / the C-ABI wrappers in api.cu)
+// =============================================================================================
+int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
+                   cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    PGPFA_TRY(set_smem_attrs());
+    FactorArgs a;
+    a.src.Kinv = ms.Kinv; a.src.W = ms.W; a.src.dense = ms.dense;
+    a.src.q = ms.q; a.src.T = ms.T; a.src.n = ms.n; a.src.diag_scale = ms.diag_scale;
+    a.L = L; a.Dinv = Dinv; a.ZT = ZT; a.act = act; a.info = info;
+    a.nb = pgpfa_nb(ms.n);
+    a.mode = 0;
+    for (int j = 0; j < a.nb; j++) {
+        a.step = j;
+        chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+        PGPFA_LAUNCH_CHECK();
+        if (j + 1 < a.nb) {
+            dim3 grid(a.nb - 1 - j, nslots);
+            chol_panel_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+            PGPFA_LAUNCH_CHECK();
+        }
+    }
+    return PGPFA_OK;
+}
+
+int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    PGPFA_TRY(set_smem_attrs());
+    FactorArgs a;
+    a.src.Kinv = nullptr; a.src.W = nullptr; a.src.dense = nullptr; a.src.q = 1; a.src.T = n; a.src.n = n; a.src.diag_scale = 1.0;
+    a.L = const_cast<double *>(L); a.Dinv = const_cast<double *>(Dinv); a.ZT = ZT; a.act = nullptr; a.info = nullptr;
+    a.nb = pgpfa_nb(n);
+    a.mode = 1;
+    for (int i = 1; i < a.nb; i++) {
+        a.step = i;
+        dim3 grid(i, nslots);
+        chol_panel_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+        PGPFA_LAUNCH_CHECK();
+    }
+    return PGPFA_OK;
+}
+
+int pgpfa_i_lauum(const double *ZT, const int2 *pairs, int npairs, const int *act, double *vsmGP, double *dense, int n,
+                  int q, int T, int nslots, cudaStream_t st) {
+    if (nslots <= 0 || npairs <= 0) return PGPFA_OK;
+    PGPFA_TRY(set_smem_attrs());
+    LauumArgs a;
+    a.ZT = ZT; a.pairs = pairs; a.act = act; a.vsmGP = vsmGP; a.dense = dense;
+    a.nb = pgpfa_nb(n); a.n = n; a.q = q; a.T = T;
+    dim3 grid(npairs, nslots);
+    lauum_tiles_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int pgpfa_i_timediag(const double *ZT, const int *act, double *vsm, int n, int q, int T, int nslots, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    const int nb = pgpfa_nb(n);
+    switch (q) {
+#define CASE_Q(QQ) case QQ: launch_timediag<QQ>(ZT, act, vsm, nb, T, nslots, st); break;
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+        default: return PGPFA_ERR_ARG;
+    }
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int pgpfa_i_logdet(const double *L, int n, int nslots, double *out, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    chol_logdet_kernel<<<nslots, 256, 0, st>>>(L, pgpfa_nb(n), n, out);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, double *out, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    dim3 grid(64, nslots);
+    tiles_to_dense_kernel<<<grid, 256, 0, st>>>(tiles, pgpfa_nb(n), n, upper, out);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}

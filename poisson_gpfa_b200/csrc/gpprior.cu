@@ -1,0 +1,227 @@
+// GP prior construction (squared-exponential kernel, one T x T block per latent) and the batched
+// SPD inverse / log-determinant used for K^-1 (funs/util.py:599-619, funs/inference.py:82,
+// funs/learning.py:183-192).  Also the C-ABI wrappers of the factorisation primitives.
+#include <vector>
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+// K[k,i,j] = (1-eps) exp(-0.5 ((i bs - j bs)^2 / (tau_k 1000)^2)) + eps delta_ij   — same operation
+// order as funs/util.py:609-614 so that the only difference is the last ulp of exp().
+__global__ void make_K_kernel(const double *__restrict__ tau, int q, int T, double bs, double eps, double *__restrict__ K) {
+    const int k = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int i = e / T, j = e - i * T;
+    const double dif = (double)i * bs - (double)j * bs;
+    const double den = (tau[k] * 1000.0) * (tau[k] * 1000.0);
+    double v = (1.0 - eps) * exp(-0.5 * ((dif * dif) / den));
+    if (i == j) v += eps;
+    K[(size_t)k * T * T + e] = v;
+}
+
+__global__ void make_K_big_kernel(const double *__restrict__ K, int q, int T, double *__restrict__ Kb) {
+    const size_t n = (size_t)q * T;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n * n; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+        const int k = r / T, l = c / T;
+        Kb[e] = (k == l) ? K[((size_t)k * T + (r - k * T)) * T + (c - l * T)] : 0.0;
+    }
+}
+
+// temp = (1-eps) exp(-exp(p)/2 difSq); K = temp + eps I; dK = -0.5 temp difSq   (funs/learning.py:183-185)
+__global__ void make_K_gamma_kernel(const double *__restrict__ p, int q, int T, double eps, double *__restrict__ K,
+                                    double *__restrict__ dK) {
+    const int k = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int i = e / T, j = e - i * T;
+    const double difSq = (double)((i - j) * (i - j));
+    const double temp = (1.0 - eps) * exp(-exp(p[k]) / 2.0 * difSq);
+    K[(size_t)k * T * T + e] = temp + (i == j ? eps : 0.0);
+    if (dK) dK[(size_t)k * T * T + e] = -0.5 * temp * difSq;
+}
+
+__global__ void hessian_dense_kernel(const double *__restrict__ Kinv, const double *__restrict__ W, double diag_scale,
+                                     int q, int T, double *__restrict__ H) {
+    const int r_ = blockIdx.y;
+    const size_t n = (size_t)q * T;
+    double *Hr = H + (size_t)r_ * n * n;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n * n; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+        const int k = r / T, s = r - k * T, l = c / T, t = c - l * T;
+        double v = 0.0;
+        if (k == l) v = Kinv[((size_t)k * T + s) * T + t];
+        if (s == t) v += W[((size_t)r_ * q * q + k * q + l) * T + t];
+        if (r == c) v *= diag_scale;
+        Hr[e] = v;
+    }
+}
+
+struct InvWs { double *L, *Dinv, *ZT; int2 *pairs; };
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int pgpfa_make_K(const double *tau, int q, int T, double bs, double eps, double *K, cudaStream_t st) {
+    if (!tau || !K || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    dim3 grid((T * T + 255) / 256, q);
+    make_K_kernel<<<grid, 256, 0, st>>>(tau, q, T, bs, eps, K);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_make_K_big(const double *K, int q, int T, double *Kb, cudaStream_t st) {
+    if (!K || !Kb || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    make_K_big_kernel<<<592, 256, 0, st>>>(K, q, T, Kb);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_make_K_gamma(const double *p, int q, int T, double eps, double *K, double *dK, cudaStream_t st) {
+    if (!p || !K || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    dim3 grid((T * T + 255) / 256, q);
+    make_K_gamma_kernel<<<grid, 256, 0, st>>>(p, q, T, eps, K, dK);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_hessian_dense(const double *Kinv, const double *W, double diag_scale, int R, int q, int T,
+                                   double *H, cudaStream_t st) {
+    if (!Kinv || !W || !H || R <= 0) return PGPFA_ERR_ARG;
+    dim3 grid(148, R);
+    hessian_dense_kernel<<<grid, 256, 0, st>>>(Kinv, W, diag_scale, q, T, H);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" long long pgpfa_tiles_bytes(int n) { return n > 0 ? pgpfa_ltiles(pgpfa_nb(n)) * PGPFA_TILE * 8 : -1; }
+extern "C" long long pgpfa_dinv_bytes(int n) { return n > 0 ? (long long)pgpfa_nb(n) * PGPFA_TILE * 8 : -1; }
+
+extern "C" long long pgpfa_spd_inverse_workspace_bytes(int batch, int n) {
+    if (batch <= 0 || n <= 0) return -1;
+    const int nb = pgpfa_nb(n);
+    return (long long)(2 * align_up((size_t)batch * pgpfa_ltiles(nb) * PGPFA_TILE * 8) +
+                       align_up((size_t)batch * nb * PGPFA_TILE * 8) + align_up(pgpfa_ltiles(nb) * sizeof(int2)) + 1024);
+}
+
+static int carve_inv_ws(void *workspace, long long ws_bytes, int batch, int n, InvWs &w) {
+    if (!workspace || ws_bytes < pgpfa_spd_inverse_workspace_bytes(batch, n)) return PGPFA_ERR_WORKSPACE;
+    const int nb = pgpfa_nb(n);
+    unsigned char *p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(workspace)));
+    const size_t tb = align_up((size_t)batch * pgpfa_ltiles(nb) * PGPFA_TILE * 8);
+    w.L = (double *)p; p += tb;
+    w.ZT = (double *)p; p += tb;
+    w.Dinv = (double *)p; p += align_up((size_t)batch * nb * PGPFA_TILE * 8);
+    w.pairs = (int2 *)p;
+    return PGPFA_OK;
+}
+
+static int upload_pairs(int2 *dst, const std::vector<int2> &pairs, cudaStream_t st) {
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(dst, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_spd_inverse_batched(const double *A, int batch, int n, double *Ainv, double *logdet, int *info,
+                                         void *workspace, long long ws_bytes, cudaStream_t st) {
+    if (!A || !Ainv || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    InvWs w;
+    PGPFA_TRY(carve_inv_ws(workspace, ws_bytes, batch, n, w));
+    std::vector<int2> pairs = pgpfa_i_cov_pairs(1, n, true);
+    PGPFA_TRY(upload_pairs(w.pairs, pairs, st));
+    if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)batch * 4, st));
+    PgpfaMatSrc ms;
+    ms.Kinv = nullptr; ms.W = nullptr; ms.dense = A; ms.q = 1; ms.T = n; ms.n = n; ms.diag_scale = 1.0;
+    PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, nullptr, info, batch, st));
+    if (logdet) PGPFA_TRY(pgpfa_i_logdet(w.L, n, batch, logdet, st));
+    PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, batch, st));
+    PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), nullptr, nullptr, Ainv, n, 1, n, batch, st));
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_potrf_dense(const double *A, int batch, int n, double *L, double *Dinv, double *ZT, int *info,
+                                 cudaStream_t st) {
+    if (!A || !L || !Dinv || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)batch * 4, st));
+    PgpfaMatSrc ms;
+    ms.Kinv = nullptr; ms.W = nullptr; ms.dense = A; ms.q = 1; ms.T = n; ms.n = n; ms.diag_scale = 1.0;
+    return pgpfa_i_factor(ms, L, Dinv, ZT, nullptr, info, batch, st);
+}
+
+extern "C" int pgpfa_potrf_posterior(const double *Kinv, const double *W, double diag_scale, int batch, int q, int T,
+                                     double *L, double *Dinv, double *ZT, int *info, cudaStream_t st) {
+    if (!Kinv || !W || !L || !Dinv || batch <= 0 || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)batch * 4, st));
+    PgpfaMatSrc ms;
+    ms.Kinv = Kinv; ms.W = W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = q * T; ms.diag_scale = diag_scale;
+    return pgpfa_i_factor(ms, L, Dinv, ZT, nullptr, info, batch, st);
+}
+
+extern "C" int pgpfa_potrs(const double *L, const double *Dinv, const double *rhs, double scale, int batch, int n,
+                           double *out, cudaStream_t st) {
+    if (!L || !Dinv || !rhs || !out || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_solve(L, Dinv, rhs, out, scale, nullptr, n, batch, st);
+}
+
+extern "C" int pgpfa_trtri(const double *L, const double *Dinv, double *ZT, int batch, int n, cudaStream_t st) {
+    if (!L || !Dinv || !ZT || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_trtri(L, Dinv, ZT, n, batch, st);
+}
+
+extern "C" int pgpfa_potri_dense(const double *ZT, int batch, int n, double *Ainv, void *workspace, long long ws_bytes,
+                                 cudaStream_t st) {
+    if (!ZT || !Ainv || !workspace || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    std::vector<int2> pairs = pgpfa_i_cov_pairs(1, n, true);
+    if ((size_t)ws_bytes < pairs.size() * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
+    int2 *dp = reinterpret_cast<int2 *>(align_up(reinterpret_cast<size_t>(workspace)));
+    PGPFA_TRY(upload_pairs(dp, pairs, st));
+    return pgpfa_i_lauum(ZT, dp, (int)pairs.size(), nullptr, nullptr, Ainv, n, 1, n, batch, st);
+}
+
+extern "C" int pgpfa_cov_slices(const double *ZT, int batch, int q, int T, double *vsm, double *vsmGP, void *workspace,
+                                long long ws_bytes, cudaStream_t st) {
+    if (!ZT || batch <= 0 || q <= 0 || q > PGPFA_QMAX || T <= 0) return PGPFA_ERR_ARG;
+    const int n = q * T;
+    if (vsm) PGPFA_TRY(pgpfa_i_timediag(ZT, nullptr, vsm, n, q, T, batch, st));
+    if (vsmGP) {
+        std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, false);
+        if (!workspace || (size_t)ws_bytes < pairs.size() * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
+        int2 *dp = reinterpret_cast<int2 *>(align_up(reinterpret_cast<size_t>(workspace)));
+        PGPFA_TRY(upload_pairs(dp, pairs, st));
+        PGPFA_TRY(pgpfa_i_lauum(ZT, dp, (int)pairs.size(), nullptr, vsmGP, nullptr, n, q, T, batch, st));
+    }
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_logdet(const double *L, int batch, int n, double *logdet, cudaStream_t st) {
+    if (!L || !logdet || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_logdet(L, n, batch, logdet, st);
+}
+
+extern "C" int pgpfa_tiles_to_dense(const double *tiles, int batch, int n, int upper, double *out, cudaStream_t st) {
+    if (!tiles || !out || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_tiles_to_dense(tiles, n, upper, batch, out, st);
+}
+
+extern "C" int pgpfa_prior_apply(const double *Kmat, const double *v, int R, int q, int T, double *out, cudaStream_t st) {
+    if (!Kmat || !v || !out || R <= 0 || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_prior_apply(Kmat, v, out, nullptr, R, q, T, st);
+}
+
+extern "C" int pgpfa_laplace_eval(const double *x, const double *y, const double *C, const double *d,
+                                  const double *Kinv, int R, int q, int N, int T, double *f, double *g, double *W,
+                                  double *Kx_ws, cudaStream_t st) {
+    if (!x || !y || !C || !d || !Kinv || !f || !g || !W || !Kx_ws || R <= 0 || q <= 0 || q > PGPFA_QMAX) return PGPFA_ERR_ARG;
+    PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, Kx_ws, nullptr, R, q, T, st));
+    return pgpfa_i_laplace_eval(x, Kx_ws, y, C, d, nullptr, R, q, N, T, f, g, W, st);
+}
+
+extern "C" int pgpfa_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
+                              cudaStream_t st) {
+    if (!vsmGP || !m || !P || R <= 0 || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    return pgpfa_i_pautosum(vsmGP, m, R, q, T, accumulate, P, st);
+}

@@ -1,0 +1,445 @@
+// Laplace E-step on device: fused rate / objective / gradient / per-bin Hessian kernel, prior
+// mat-vec, backtracking line search, active-trial compaction, and the host-side Newton driver.
+// Reference: funs/inference.py:12-65 (objective, gradient, Hessian) and :67-185 (per-trial loop).
+// The reference materialises C_big (qT x NT); here everything is per-bin (SURVEY.md §8a identities):
+//   h[n,t] = sum_k C[n,k] x[k,t] + d[n]            lam = exp(h)
+//   f      = sum lam - y h + 0.5 x^T Kinv x
+//   g[k,t] = sum_n C[n,k] (lam - y)[n,t] + (Kinv_k x_k)[t]
+//   W[k,l,t] = sum_n C[n,k] C[n,l] lam[n,t]        (H = blkdiag(Kinv) + scatter(W))
+#include <vector>
+#include <set>
+#include <utility>
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+// out[trial,k,s] = sum_t Kinv[k,s,t] v[trial,k,t]   (Kinv symmetric: read column-wise, coalesced)
+#define PA_TR 8
+__global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
+                                                          double *__restrict__ out, const int *act, int nslots, int q,
+                                                          int T) {
+    extern __shared__ double vs[];   // PA_TR x T
+    __shared__ int trial[PA_TR];
+    const int k = blockIdx.x;
+    const int s0 = blockIdx.y * PA_TR;
+    if (threadIdx.x < PA_TR) {
+        const int slot = s0 + threadIdx.x;
+        trial[threadIdx.x] = slot < nslots ? (act ? act[slot] : slot) : -1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PA_TR * T; i += blockDim.x) {
+        const int r = i / T, t = i - r * T;
+        const int tr = trial[r];
+        vs[i] = tr >= 0 ? v[((size_t)tr * q + k) * T + t] : 0.0;
+    }
+    __syncthreads();
+    const double *Kk = Kmat + (size_t)k * T * T;
+    for (int s = threadIdx.x; s < T; s += blockDim.x) {
+        double acc[PA_TR];
+#pragma unroll
+        for (int r = 0; r < PA_TR; r++) acc[r] = 0.0;
+        for (int t = 0; t < T; t++) {
+            const double kv = Kk[(size_t)t * T + s];
+#pragma unroll
+            for (int r = 0; r < PA_TR; r++) acc[r] += kv * vs[r * T + t];
+        }
+#pragma unroll
+        for (int r = 0; r < PA_TR; r++)
+            if (trial[r] >= 0) out[((size_t)trial[r] * q + k) * T + s] = acc[r];
+    }
+}
+
+// fused rates + objective + gradient + per-bin Hessian blocks; one CTA per trial, thread <-> bin
+template <int Q>
+__global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restrict__ x, const double *__restrict__ Kx,
+                                                           const double *__restrict__ y, const double *__restrict__ C,
+                                                           const double *__restrict__ d, const int *act, int N, int T,
+                                                           double *__restrict__ f, double *__restrict__ g,
+                                                           double *__restrict__ W) {
+    extern __shared__ double sm[];
+    double *Cs = sm;             // N*Q
+    double *ds = sm + N * Q;     // N
+    __shared__ double red[32];
+    const int trial = act ? act[blockIdx.x] : blockIdx.x;
+    for (int i = threadIdx.x; i < N * Q; i += blockDim.x) Cs[i] = C[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ds[i] = d[i];
+    __syncthreads();
+    double fl = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double xk[Q], gk[Q], w[Q * (Q + 1) / 2];
+#pragma unroll
+        for (int k = 0; k < Q; k++) { xk[k] = x[((size_t)trial * Q + k) * T + t]; gk[k] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < Q * (Q + 1) / 2; i++) w[i] = 0.0;
+        const double *yp = y + (size_t)trial * N * T + t;
+        for (int n = 0; n < N; n++) {
+            double h = ds[n];
+#pragma unroll
+            for (int k = 0; k < Q; k++) h += Cs[n * Q + k] * xk[k];
+            const double lam = exp(h);
+            const double yy = yp[(size_t)n * T];
+            fl += lam - yy * h;
+            const double r = lam - yy;
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                const double ck = Cs[n * Q + k];
+                gk[k] += ck * r;
+                const double cl = ck * lam;
+#pragma unroll
+                for (int l = k; l < Q; l++) { w[idx] += cl * Cs[n * Q + l]; idx++; }
+            }
+        }
+        int idx = 0;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            const double kx = Kx[((size_t)trial * Q + k) * T + t];
+            fl += 0.5 * xk[k] * kx;
+            g[((size_t)trial * Q + k) * T + t] = gk[k] + kx;
+#pragma unroll
+            for (int l = k; l < Q; l++) {
+                W[((size_t)trial * Q * Q + k * Q + l) * T + t] = w[idx];
+                if (l != k) W[((size_t)trial * Q * Q + l * Q + k) * T + t] = w[idx];
+                idx++;
+            }
+        }
+    }
+    fl = block_sum(fl, red);
+    if (threadIdx.x == 0) f[trial] = fl;
+}
+
+// Armijo backtracking along the Newton direction; updates x in place and sets convergence flags.
+template <int Q>
+__global__ void __launch_bounds__(256) laplace_linesearch_kernel(
+    double *__restrict__ x, const double *__restrict__ dx, const double *__restrict__ Kx, const double *__restrict__ Kd,
+    const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
+    const double *__restrict__ d, const int *act, int N, int T, double tol, double *__restrict__ fcur,
+    int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen) {
+    extern __shared__ double sm[];
+    double *Cs = sm;
+    double *ds = sm + N * Q;
+    __shared__ double red[32];
+    const int trial = act ? act[blockIdx.x] : blockIdx.x;
+    for (int i = threadIdx.x; i < N * Q; i += blockDim.x) Cs[i] = C[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ds[i] = d[i];
+    __syncthreads();
+    const size_t base = (size_t)trial * Q * T;
+    double slope = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, dmax = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
+        const double xv = x[base + i], dv = dx[base + i], kx = Kx[base + i], kd = Kd[base + i];
+        slope += g[base + i] * dv;
+        a0 += xv * kx;
+        a1 += dv * kx;
+        a2 += dv * kd;
+        dmax = fmax(dmax, fabs(dv));
+    }
+    slope = block_sum(slope, red);
+    a0 = block_sum(a0, red);
+    a1 = block_sum(a1, red);
+    a2 = block_sum(a2, red);
+    dmax = block_max(dmax, red);
+    const double f0 = fcur[trial];
+    const bool tiny = fabs(slope) <= 1e-9 * (1.0 + fabs(f0));
+    double alpha = 1.0, fnew = f0;
+    for (int ls = 0; ls < 40; ls++) {
+        double fl = 0.0;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            double xk[Q], dk[Q];
+#pragma unroll
+            for (int k = 0; k < Q; k++) { xk[k] = x[base + (size_t)k * T + t]; dk[k] = dx[base + (size_t)k * T + t]; }
+            const double *yp = y + (size_t)trial * N * T + t;
+            for (int n = 0; n < N; n++) {
+                double h = ds[n], dh = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; k++) { h += Cs[n * Q + k] * xk[k]; dh += Cs[n * Q + k] * dk[k]; }
+                const double ha = h + alpha * dh;
+                fl += exp(ha) - yp[(size_t)n * T] * ha;
+            }
+        }
+        fl = block_sum(fl, red);
+        fnew = fl + 0.5 * a0 + alpha * a1 + 0.5 * alpha * alpha * a2;
+        const bool ok = isfinite(fnew) && (tiny || fnew <= f0 + 1e-4 * alpha * slope + 1e-13 * (1.0 + fabs(f0)));
+        if (ok) break;
+        alpha *= 0.5;
+    }
+    double xmax = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
+        const double xn = x[base + i] + alpha * dx[base + i];
+        x[base + i] = xn;
+        xmax = fmax(xmax, fabs(xn));
+    }
+    xmax = block_max(xmax, red);
+    if (threadIdx.x == 0) {
+        fcur[trial] = fnew;
+        const double sl = alpha * dmax;
+        steplen[trial] = sl;
+        conv[trial] = (sl <= tol * (1.0 + xmax)) ? 1 : 0;
+        niter[trial] += 1;
+    }
+}
+
+// ordered compaction of the not-yet-converged trials (single CTA)
+__global__ void __launch_bounds__(1024) compact_active_kernel(const int *__restrict__ act_in, int n_in,
+                                                              const int *__restrict__ conv, int *__restrict__ act_out,
+                                                              int *__restrict__ n_out) {
+    __shared__ int wsum[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int b = 0; b < n_in; b += 1024) {
+        const int i = b + tid;
+        int trial = -1, keep = 0;
+        if (i < n_in) { trial = act_in[i]; keep = conv[trial] ? 0 : 1; }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int wpre = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < warp; w++) off += wsum[w];
+        if (keep) act_out[off + wpre] = trial;
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += wsum[w]; running += tot; }
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = running;
+}
+
+__global__ void iota_kernel(int *p, int n, int start) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = start + i;
+}
+
+// PautoSum[k,s,t] (+)= sum_r vsmGP[r,k,s,t] + m[r,k,s] m[r,k,t]     (funs/learning.py:162-165)
+__global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict__ vsmGP, const double *__restrict__ m,
+                                                       int R, int q, int T, int accumulate, double *__restrict__ P) {
+    const int k = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int s = e / T, t = e - s * T;
+    double a0 = 0.0, a1 = 0.0;
+    const size_t strideV = (size_t)q * T * T, strideM = (size_t)q * T;
+    const double *vp = vsmGP + (size_t)k * T * T + e;
+    const double *mp = m + (size_t)k * T;
+    int r = 0;
+    for (; r + 1 < R; r += 2) {
+        a0 += vp[(size_t)r * strideV] + mp[(size_t)r * strideM + s] * mp[(size_t)r * strideM + t];
+        a1 += vp[(size_t)(r + 1) * strideV] + mp[(size_t)(r + 1) * strideM + s] * mp[(size_t)(r + 1) * strideM + t];
+    }
+    if (r < R) a0 += vp[(size_t)r * strideV] + mp[(size_t)r * strideM + s] * mp[(size_t)r * strideM + t];
+    double *o = P + (size_t)k * T * T + e;
+    *o = (accumulate ? *o : 0.0) + (a0 + a1);
+}
+
+template <int Q>
+int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const int *act,
+                int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st) {
+    const size_t smem = (size_t)(N * Q + N) * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, act, N, T, f, g, W);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+template <int Q>
+int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
+                      const double *C, const double *d, const int *act, int nslots, int N, int T, double tol,
+                      double *fcur, int *conv, int *niter, double *steplen, cudaStream_t st) {
+    const size_t smem = (size_t)(N * Q + N) * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, act, N, T, tol, fcur, conv, niter, steplen);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+}  // namespace
+
+int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
+                        cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    const size_t smem = (size_t)PA_TR * T * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(prior_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q, (nslots + PA_TR - 1) / PA_TR);
+    prior_apply_kernel<<<grid, 256, smem, st>>>(Kmat, v, out, act, nslots, q, T);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
+                         const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
+                         cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    switch (q) {
+#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, act, nslots, N, T, f, g, W, st);
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+    }
+    return PGPFA_ERR_ARG;
+}
+
+int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
+                       const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
+                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    switch (q) {
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, act, nslots, N, T, tol, fcur, conv, niter, steplen, st);
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+    }
+    return PGPFA_ERR_ARG;
+}
+
+int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
+                     cudaStream_t st) {
+    if (R <= 0) return PGPFA_OK;
+    dim3 grid((T * T + 255) / 256, q);
+    pautosum_kernel<<<grid, 256, 0, st>>>(vsmGP, m, R, q, T, accumulate, P);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all) {
+    const int n = q * T, nb = pgpfa_nb(n);
+    std::set<std::pair<int, int>> s;
+    if (all) {
+        for (int a = 0; a < nb; a++) for (int b = 0; b <= a; b++) s.insert({a, b});
+    } else {
+        for (int k = 0; k < q; k++) {
+            const int lo = (k * T) >> 6, hi = (k * T + T - 1) >> 6;
+            for (int a = lo; a <= hi; a++) for (int b = lo; b <= a; b++) s.insert({a, b});
+        }
+    }
+    std::vector<int2> out;
+    // heavy tiles (small a => long k-loop) first
+    for (auto &p : s) out.push_back(make_int2(p.first, p.second));
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout of the Laplace driver
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LapWs {
+    double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen;
+    int *conv, *actA, *actB, *cnt;
+    int2 *pairs;
+    double *L, *Dinv, *ZT;
+    int chunk;
+};
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
+    const size_t n = (size_t)q * T;
+    size_t b = 0;
+    b += 4 * align_up((size_t)R * n * 8);
+    b += align_up((size_t)R * q * q * T * 8);
+    b += 2 * align_up((size_t)R * 8);
+    b += 3 * align_up((size_t)R * 4) + 256;
+    b += align_up((size_t)npairs_max * sizeof(int2));
+    return b;
+}
+size_t lap_per_trial_bytes(int q, int T) {
+    const int nb = pgpfa_nb(q * T);
+    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8;
+}
+}  // namespace
+
+extern "C" long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chunk) {
+    if (R <= 0 || q <= 0 || T <= 0) return -1;
+    if (chunk <= 0 || chunk > R) chunk = R;
+    const int nb = pgpfa_nb(q * T);
+    return (long long)(lap_fixed_bytes(R, q, T, (int)pgpfa_ltiles(nb)) + (size_t)chunk * lap_per_trial_bytes(q, T) + 4096);
+}
+
+extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d,
+                                   const double *Kinv, double *x, int R, int q, int N, int T, double tol,
+                                   int max_newton, double *f_out, double *vsm, double *vsmGP, double *cov_dense,
+                                   int *niter, int *info, void *workspace, long long ws_bytes, int *stats_out,
+                                   cudaStream_t st) {
+    if (!h || !y || !C || !d || !Kinv || !x || !f_out || !niter || !info || !workspace) return PGPFA_ERR_ARG;
+    if (R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0 || max_newton <= 0) return PGPFA_ERR_ARG;
+    const int n = q * T, nb = pgpfa_nb(n);
+    const long long ltl = pgpfa_ltiles(nb);
+    const size_t fixed = lap_fixed_bytes(R, q, T, (int)ltl);
+    const size_t per = lap_per_trial_bytes(q, T);
+    if ((size_t)ws_bytes < fixed + per) return PGPFA_ERR_WORKSPACE;
+    long long chunk_ll = ((size_t)ws_bytes - fixed) / per;
+    const int chunk = (int)(chunk_ll > R ? R : chunk_ll);
+
+    unsigned char *p = static_cast<unsigned char *>(workspace);
+    p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(p)));
+    LapWs w;
+    auto take = [&](size_t bytes) { unsigned char *r = p; p += align_up(bytes); return r; };
+    const size_t vec = (size_t)R * n * 8;
+    w.Kx = (double *)take(vec); w.Kd = (double *)take(vec); w.g = (double *)take(vec); w.dx = (double *)take(vec);
+    w.W = (double *)take((size_t)R * q * q * T * 8);
+    w.fcur = (double *)take((size_t)R * 8); w.steplen = (double *)take((size_t)R * 8);
+    w.conv = (int *)take((size_t)R * 4); w.actA = (int *)take((size_t)R * 4); w.actB = (int *)take((size_t)R * 4);
+    w.cnt = (int *)take(256);
+    w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
+    w.L = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
+    w.Dinv = (double *)take((size_t)chunk * nb * PGPFA_TILE * 8);
+    w.ZT = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
+
+    PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
+    PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
+    std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, cov_dense != nullptr);
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(w.pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));   // pairs is a host temporary
+
+    PgpfaMatSrc ms;
+    ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
+    int total_factor_trials = 0, max_it_used = 0, not_converged = 0;
+    for (int c0 = 0; c0 < R; c0 += chunk) {
+        const int cn = (R - c0) < chunk ? (R - c0) : chunk;
+        iota_kernel<<<(cn + 255) / 256, 256, 0, st>>>(w.actA, cn, c0);
+        PGPFA_LAUNCH_CHECK();
+        int *act = w.actA, *act_next = w.actB;
+        int n_act = cn;
+        for (int it = 0; it < max_newton && n_act > 0; it++) {
+            PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
+            PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st));
+            PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, act, n, n_act, st));
+            PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
+            PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
+                                         niter, w.steplen, st));
+            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, act_next, w.cnt);
+            PGPFA_LAUNCH_CHECK();
+            total_factor_trials += n_act;
+            PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+            n_act = h->pinned[0];
+            int *tmp = act; act = act_next; act_next = tmp;
+            if (it + 1 > max_it_used) max_it_used = it + 1;
+        }
+        not_converged += n_act;
+        // posterior at the mode: objective, factor, inverse slices
+        iota_kernel<<<(cn + 255) / 256, 256, 0, st>>>(w.actA, cn, c0);
+        PGPFA_LAUNCH_CHECK();
+        PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, w.actA, cn, q, T, st));
+        PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, w.actA, cn, q, N, T, f_out, w.g, w.W, st));
+        if (vsm || vsmGP || cov_dense) {
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st));
+            total_factor_trials += cn;
+            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st));
+            if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
+            if (vsmGP || cov_dense)
+                PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,
+                                        cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
+        }
+    }
+    if (stats_out) {
+        stats_out[0] = total_factor_trials;
+        stats_out[1] = max_it_used;
+        stats_out[2] = not_converged;
+        stats_out[3] = chunk;
+    }
+    return not_converged ? PGPFA_ERR_NOT_CONVERGED : PGPFA_OK;
+}

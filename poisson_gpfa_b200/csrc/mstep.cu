@@ -1,0 +1,382 @@
+// M-step kernels.
+//  * C,d: the reference minimises MStepObservationCost (funs/learning.py:20-91) with scipy; the cost
+//    is separable over neurons and convex, so here every neuron runs its own (q+1)-dimensional damped
+//    Newton.  One pass over (y, post_mean, post_vsm) produces per-neuron cost / gradient / Hessian
+//    sums (HBM-bound streaming reduction, deterministic two-stage sum); the per-neuron update kernel
+//    does accept/reject + the next Newton step.  Between the two the host all-reduces `stats` across
+//    GPUs (trial sharding).
+//  * tau: cost and gradient of MStepGPtimescaleCost (funs/learning.py:175-255, prior variant
+//    :681-769) for all latents at once, on the batched SPD inverse.
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+#define CD_TT 16   // bins per work item
+
+template <int Q>
+__global__ void __launch_bounds__(256) mstep_cd_stats_kernel(const double *__restrict__ y, const double *__restrict__ m,
+                                                             const double *__restrict__ vsm,
+                                                             const double *__restrict__ theta, int R, int N, int T,
+                                                             double *__restrict__ partial) {
+    constexpr int P = Q + 1;
+    constexpr int NS = 1 + P + P * (P + 1) / 2;
+    extern __shared__ double sm[];
+    double *ys = sm;                          // N x (CD_TT+1)
+    double *ms = ys + (size_t)N * (CD_TT + 1);  // Q x CD_TT
+    double *vs = ms + Q * CD_TT;              // CD_TT x Q*Q
+    const int nTT = (T + CD_TT - 1) / CD_TT;
+    const long long items = (long long)R * nTT;
+    const int nloc = threadIdx.x;             // neuron handled by this thread (block covers 256 neurons per pass)
+    for (int n0 = 0; n0 < N; n0 += blockDim.x) {
+        const int n = n0 + nloc;
+        const bool live = n < N;
+        double c[Q], dd = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; k++) c[k] = live ? theta[(size_t)n * P + k] : 0.0;
+        if (live) dd = theta[(size_t)n * P + Q];
+        double st[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) st[i] = 0.0;
+        for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+            const int r = (int)(item / nTT);
+            const int t0 = (int)(item - (long long)r * nTT) * CD_TT;
+            const int tl = (T - t0) < CD_TT ? (T - t0) : CD_TT;
+            __syncthreads();
+            for (int i = threadIdx.x; i < N * CD_TT; i += blockDim.x) {
+                const int nn = i / CD_TT, tt = i - nn * CD_TT;
+                ys[nn * (CD_TT + 1) + tt] = tt < tl ? y[((size_t)r * N + nn) * T + t0 + tt] : 0.0;
+            }
+            for (int i = threadIdx.x; i < Q * CD_TT; i += blockDim.x) {
+                const int k = i / CD_TT, tt = i - k * CD_TT;
+                ms[i] = tt < tl ? m[((size_t)r * Q + k) * T + t0 + tt] : 0.0;
+            }
+            for (int i = threadIdx.x; i < CD_TT * Q * Q; i += blockDim.x)
+                vs[i] = (i / (Q * Q)) < tl ? vsm[((size_t)r * T + t0) * Q * Q + i] : 0.0;
+            __syncthreads();
+            if (live) {
+                for (int tt = 0; tt < tl; tt++) {
+                    double vc[Q], u[Q];
+                    double h = dd, s = 0.0;
+                    const double *V = vs + tt * Q * Q;
+#pragma unroll
+                    for (int k = 0; k < Q; k++) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int l = 0; l < Q; l++) a += V[k * Q + l] * c[l];
+                        vc[k] = a;
+                        s += c[k] * a;
+                        const double mk = ms[k * CD_TT + tt];
+                        h += c[k] * mk;
+                        u[k] = mk + a;
+                    }
+                    const double yh = exp(h + 0.5 * s);
+                    const double yv = ys[n * (CD_TT + 1) + tt];
+                    st[0] += yh - yv * h;
+                    int idx = 1 + P;
+#pragma unroll
+                    for (int k = 0; k < Q; k++) {
+                        const double yu = yh * u[k];
+                        st[1 + k] += yu - yv * ms[k * CD_TT + tt];
+#pragma unroll
+                        for (int l = k; l < Q; l++) { st[idx] += yu * u[l] + yh * V[k * Q + l]; idx++; }
+                        st[idx] += yu;   // H[k][d]
+                        idx++;
+                    }
+                    st[1 + Q] += yh - yv;
+                    st[idx] += yh;       // H[d][d]
+                }
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) partial[((size_t)blockIdx.x * NS + i) * N + n] = st[i];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void mstep_cd_reduce_kernel(const double *__restrict__ partial, int nblocks, int len, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * len + i];
+    out[i] = s;
+}
+
+// per-neuron accept/reject and next Newton step.  State arrays are (N) or (N, q+1).
+template <int Q>
+__global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double invR, double pw,
+                                       const double *__restrict__ theta0, double *__restrict__ theta_cur,
+                                       double *__restrict__ theta_try, double *__restrict__ fcur,
+                                       double *__restrict__ step, double *__restrict__ alpha,
+                                       double *__restrict__ slope, int *__restrict__ done, int first, double tol, int N,
+                                       int *__restrict__ n_open) {
+    constexpr int P = Q + 1;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    if (done[n]) return;
+    double tt[P], t0[P];
+    double pen = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        tt[k] = theta_try[(size_t)n * P + k];
+        t0[k] = theta0[(size_t)n * P + k];
+        pen += (tt[k] - t0[k]) * (tt[k] - t0[k]);
+    }
+    const double ftry = stats[n] * invR + 0.5 * pw * pen;
+    bool accept = first != 0;
+    if (!accept) {
+        const double f0 = fcur[n], sl = slope[n], al = alpha[n];
+        const bool tiny = fabs(sl) <= 1e-10 * (1.0 + fabs(f0));
+        accept = isfinite(ftry) && (tiny || ftry <= f0 + 1e-4 * al * sl + 1e-14 * (1.0 + fabs(f0)));
+        if (!accept && al < 1e-12) accept = isfinite(ftry);   // give up backtracking, keep going
+    }
+    if (!accept) {
+        const double al = 0.5 * alpha[n];
+        alpha[n] = al;
+#pragma unroll
+        for (int k = 0; k < P; k++) theta_try[(size_t)n * P + k] = theta_cur[(size_t)n * P + k] + al * step[(size_t)n * P + k];
+        atomicAdd(n_open, 1);
+        return;
+    }
+    // accepted: gradient / Hessian at theta_try, Cholesky solve of the (q+1) system
+    double g[P], H[P][P];
+#pragma unroll
+    for (int k = 0; k < P; k++) g[k] = stats[(size_t)(1 + k) * N + n] * invR + pw * (tt[k] - t0[k]);
+    {
+        int idx = 1 + P;
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+            for (int l = k; l < P; l++) {
+                const double v = stats[(size_t)idx * N + n] * invR + ((k == l) ? pw : 0.0);
+                H[k][l] = v;
+                H[l][k] = v;
+                idx++;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        double dj = H[j][j];
+#pragma unroll
+        for (int k = 0; k < P; k++) if (k < j) dj -= H[j][k] * H[j][k];
+        dj = sqrt(fmax(dj, 1e-300));
+        H[j][j] = dj;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            if (i > j) {
+                double v = H[i][j];
+#pragma unroll
+                for (int k = 0; k < P; k++) if (k < j) v -= H[i][k] * H[j][k];
+                H[i][j] = v / dj;
+            }
+    }
+    double z[P], dl[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double v = -g[i];
+#pragma unroll
+        for (int k = 0; k < P; k++) if (k < i) v -= H[i][k] * z[k];
+        z[i] = v / H[i][i];
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; i--) {
+        double v = z[i];
+#pragma unroll
+        for (int k = 0; k < P; k++) if (k > i) v -= H[k][i] * dl[k];
+        dl[i] = v / H[i][i];
+    }
+    double sl = 0.0, dmax = 0.0, tmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; k++) { sl += g[k] * dl[k]; dmax = fmax(dmax, fabs(dl[k])); tmax = fmax(tmax, fabs(tt[k])); }
+    fcur[n] = ftry;
+    slope[n] = sl;
+    alpha[n] = 1.0;
+    const bool conv = dmax <= tol * (1.0 + tmax);
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        step[(size_t)n * P + k] = dl[k];
+        const double nx = tt[k] + dl[k];
+        theta_cur[(size_t)n * P + k] = conv ? nx : tt[k];
+        theta_try[(size_t)n * P + k] = nx;
+    }
+    if (conv) done[n] = 1;
+    else atomicAdd(n_open, 1);
+}
+
+// C = A * B for a batch of row-major n x n matrices (small FP64 GEMM, 64x64 tiles, 16x16 threads)
+__global__ void __launch_bounds__(256) small_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                         double *__restrict__ Cm, int n) {
+    __shared__ double As[64][17], Bs[16][65];
+    const int b = blockIdx.z;
+    const double *Ab = A + (size_t)b * n * n, *Bb = B + (size_t)b * n * n;
+    double *Cb = Cm + (size_t)b * n * n;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int rr = i >> 4, kk = i & 15;
+            As[rr][kk] = (r0 + rr < n && k0 + kk < n) ? Ab[(size_t)(r0 + rr) * n + k0 + kk] : 0.0;
+            const int k2 = i >> 6, cc = i & 63;
+            Bs[k2][cc] = (k0 + k2 < n && c0 + cc < n) ? Bb[(size_t)(k0 + k2) * n + c0 + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[ty * 4 + i][kk];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] += a[i] * bb[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
+            if (r < n && c < n) Cb[(size_t)r * n + c] = acc[i][j];
+        }
+}
+
+// cost / gradient of the timescale objective from Kinv, logdet, dK, G = Kinv dK Kinv and PautoSum
+__global__ void __launch_bounds__(256) tau_reduce_kernel(const double *__restrict__ p, const double *__restrict__ Kinv,
+                                                         const double *__restrict__ dK, const double *__restrict__ G,
+                                                         const double *__restrict__ P, const double *__restrict__ logdet,
+                                                         double R, int T, double pw, const double *__restrict__ tau_old,
+                                                         double bs, double *__restrict__ cost, double *__restrict__ grad) {
+    __shared__ double red[32];
+    const int k = blockIdx.x;
+    const size_t off = (size_t)k * T * T;
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const double ki = Kinv[off + e], pp = P[off + e];
+        t1 += ki * pp;
+        t2 += ki * dK[off + e];
+        t3 += G[off + e] * pp;
+    }
+    t1 = block_sum(t1, red);
+    t2 = block_sum(t2, red);
+    t3 = block_sum(t3, red);
+    if (threadIdx.x == 0) {
+        double c = 0.5 * R * logdet[k] + 0.5 * t1;
+        const double dE = -0.5 * R * t2 + 0.5 * t3;
+        double g = -dE * exp(p[k]);
+        if (pw > 0.0) {
+            const double tau = bs / 1000.0 * sqrt(1.0 / exp(p[k]));
+            const double dt = tau - tau_old[k];
+            c += 0.5 * dt * dt * pw;
+            g += dt * pw;      // as written in funs/learning.py:734,769 (no chain-rule factor)
+        }
+        cost[k] = c;
+        grad[k] = g;
+    }
+}
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+inline int cd_blocks() { return 148 * 3; }
+inline int cd_threads(int N) { int t = ((N + 31) / 32) * 32; return t > 256 ? 256 : t; }
+
+template <int Q>
+int launch_cd_stats(const double *y, const double *m, const double *vsm, const double *theta, int R, int N, int T,
+                    double *partial, int nblocks, cudaStream_t st) {
+    const size_t smem = ((size_t)N * (CD_TT + 1) + Q * CD_TT + CD_TT * Q * Q) * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(mstep_cd_stats_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mstep_cd_stats_kernel<Q><<<nblocks, cd_threads(N), smem, st>>>(y, m, vsm, theta, R, N, T, partial);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+}  // namespace
+
+extern "C" int pgpfa_mstep_cd_nstats(int q) { return 1 + (q + 1) + (q + 1) * (q + 2) / 2; }
+
+extern "C" long long pgpfa_mstep_cd_workspace_bytes(int q, int N) {
+    if (q <= 0 || N <= 0) return -1;
+    return (long long)align_up((size_t)cd_blocks() * pgpfa_mstep_cd_nstats(q) * N * 8) + 512;
+}
+
+extern "C" int pgpfa_mstep_cd_stats(const double *y, const double *m, const double *vsm, const double *theta, int R,
+                                    int q, int N, int T, double *stats, void *workspace, long long ws_bytes,
+                                    cudaStream_t st) {
+    if (!y || !m || !vsm || !theta || !stats || !workspace || R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0)
+        return PGPFA_ERR_ARG;
+    if (ws_bytes < pgpfa_mstep_cd_workspace_bytes(q, N)) return PGPFA_ERR_WORKSPACE;
+    double *partial = reinterpret_cast<double *>(align_up(reinterpret_cast<size_t>(workspace)));
+    const long long items = (long long)R * ((T + CD_TT - 1) / CD_TT);
+    int nblocks = cd_blocks();
+    if (items < nblocks) nblocks = (int)items;
+    int rc = PGPFA_ERR_ARG;
+    switch (q) {
+#define CASE_Q(QQ) case QQ: rc = launch_cd_stats<QQ>(y, m, vsm, theta, R, N, T, partial, nblocks, st); break;
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+    }
+    PGPFA_TRY(rc);
+    const int len = pgpfa_mstep_cd_nstats(q) * N;
+    mstep_cd_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(partial, nblocks, len, stats);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *theta0,
+                                     double *theta_cur, double *theta_try, double *fcur, double *step, double *alpha,
+                                     double *slope, int *done, int first, double tol, int N, int q, int *n_open,
+                                     cudaStream_t st) {
+    if (!stats || !theta0 || !theta_cur || !theta_try || !fcur || !step || !alpha || !slope || !done || !n_open)
+        return PGPFA_ERR_ARG;
+    PGPFA_CUDA_TRY(cudaMemsetAsync(n_open, 0, sizeof(int), st));
+    const int blocks = (N + 63) / 64;
+    switch (q) {
+#define CASE_Q(QQ) case QQ: mstep_cd_update_kernel<QQ><<<blocks, 64, 0, st>>>(stats, inv_R, prior_w, theta0, theta_cur, theta_try, fcur, step, alpha, slope, done, first, tol, N, n_open); break;
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+        default: return PGPFA_ERR_ARG;
+    }
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" long long pgpfa_tau_eval_workspace_bytes(int q, int T) {
+    if (q <= 0 || T <= 0) return -1;
+    const size_t mat = align_up((size_t)q * T * T * 8);
+    return (long long)(5 * mat + align_up((size_t)q * 8) + align_up((size_t)q * 4)) + pgpfa_spd_inverse_workspace_bytes(q, T) + 1024;
+}
+
+extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTrials, int q, int T, double eps,
+                              double prior_w, const double *tau_old, double bs, double *cost, double *grad,
+                              void *workspace, long long ws_bytes, cudaStream_t st) {
+    if (!p || !Psum || !cost || !grad || !workspace || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
+    if (prior_w > 0.0 && !tau_old) return PGPFA_ERR_ARG;
+    if (ws_bytes < pgpfa_tau_eval_workspace_bytes(q, T)) return PGPFA_ERR_WORKSPACE;
+    unsigned char *w = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(workspace)));
+    const size_t mat = align_up((size_t)q * T * T * 8);
+    double *K = (double *)w; w += mat;
+    double *dK = (double *)w; w += mat;
+    double *Kinv = (double *)w; w += mat;
+    double *M1 = (double *)w; w += mat;
+    double *G = (double *)w; w += mat;
+    double *logdet = (double *)w; w += align_up((size_t)q * 8);
+    int *info = (int *)w; w += align_up((size_t)q * 4);
+    const long long inv_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
+    PGPFA_TRY(pgpfa_make_K_gamma(p, q, T, eps, K, dK, st));
+    PGPFA_TRY(pgpfa_spd_inverse_batched(K, q, T, Kinv, logdet, info, w, inv_bytes, st));
+    dim3 grid((T + 63) / 64, (T + 63) / 64, q);
+    small_gemm_kernel<<<grid, 256, 0, st>>>(Kinv, dK, M1, T);
+    PGPFA_LAUNCH_CHECK();
+    small_gemm_kernel<<<grid, 256, 0, st>>>(M1, Kinv, G, T);
+    PGPFA_LAUNCH_CHECK();
+    tau_reduce_kernel<<<q, 256, 0, st>>>(p, Kinv, dK, G, Psum, logdet, numTrials, T, prior_w, tau_old, bs, cost, grad);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}

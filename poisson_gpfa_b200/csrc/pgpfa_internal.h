@@ -1,0 +1,46 @@
+// Internal host-side interfaces between the translation units of libpgpfa_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+// latent dimensionalities with compiled kernels (accumulator counts depend on q)
+#define PGPFA_FOR_EACH_Q(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#define PGPFA_QMAX 12
+
+struct PgpfaMatSrc {
+    const double *Kinv;   // (q,T,T) generator mode; nullptr => dense mode
+    const double *W;      // (trials, q*q, T)
+    const double *dense;  // (slots, n, n)
+    int q, T, n;
+    double diag_scale;
+};
+
+int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
+                   cudaStream_t st);
+int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st);
+int pgpfa_i_lauum(const double *ZT, const int2 *pairs, int npairs, const int *act, double *vsmGP, double *dense, int n,
+                  int q, int T, int nslots, cudaStream_t st);
+int pgpfa_i_timediag(const double *ZT, const int *act, double *vsm, int n, int q, int T, int nslots, cudaStream_t st);
+int pgpfa_i_logdet(const double *L, int n, int nslots, double *out, cudaStream_t st);
+int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, double *out, cudaStream_t st);
+int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
+                  int n, int nslots, cudaStream_t st);
+
+#include <vector>
+#include "../../include/pgpfa_b200.h"
+
+struct pgpfa_handle_s {
+    int *pinned;        // small pinned host scratch for device -> host counters
+    int device;
+};
+
+int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
+                        cudaStream_t st);
+int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
+                         const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
+                         cudaStream_t st);
+int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
+                       const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
+                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, cudaStream_t st);
+int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
+                     cudaStream_t st);
+std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);

@@ -1,0 +1,125 @@
+// Batched triangular solves with the tiled Cholesky factor:  out = scale * (L L^T)^-1 rhs.
+// This is the Newton step of the Laplace E-step (replaces the inner CG of scipy's Newton-CG at
+// funs/inference.py:119-126).  HBM-bound: each trial's factor (packed 64x64 tiles) is streamed
+// twice (forward + backward), once per Newton iteration.  One CTA per trial, 8 warps; the diagonal
+// blocks are applied through their explicit inverses (Dinv) produced by the factorisation.
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+__global__ void __launch_bounds__(256) chol_solve_kernel(const double *__restrict__ L, const double *__restrict__ Dinv,
+                                                         const double *__restrict__ rhs, double *__restrict__ out,
+                                                         double scale, const int *act, int nb, int n) {
+    extern __shared__ double sm[];
+    double *z = sm;                 // nb*64
+    double *tmp = sm + nb * PGPFA_NB;  // 64
+    const int slot = blockIdx.x;
+    const int trial = act ? act[slot] : slot;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long ltl = (long long)nb * (nb + 1) / 2;
+    const double *Ls = L + (size_t)slot * ltl * PGPFA_TILE;
+    const double *Ds = Dinv + (size_t)slot * nb * PGPFA_TILE;
+    for (int i = tid; i < nb * PGPFA_NB; i += 256) z[i] = (i < n) ? rhs[(size_t)trial * n + i] : 0.0;
+    __syncthreads();
+    const int c2 = 2 * (lane & 3);
+    // ---- forward: L y = rhs
+    for (int j = 0; j < nb; j++) {
+        const double *row = Ls + ltile(j, 0) * PGPFA_TILE + w * 64 + lane * 2;
+        double acc = 0.0;
+        for (int k = 0; k < j; k++) {
+            const double *tp = row + (size_t)k * PGPFA_TILE;
+            const double *zp = z + k * PGPFA_NB + c2;
+#pragma unroll
+            for (int sp = 0; sp < 8; sp++) {
+                const double2 a = *reinterpret_cast<const double2 *>(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
+                const double2 v = *reinterpret_cast<const double2 *>(zp + sp * 8);
+                acc += a.x * v.x + a.y * v.y;
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if ((lane & 3) == 0) tmp[w * 8 + (lane >> 2)] = z[j * PGPFA_NB + w * 8 + (lane >> 2)] - acc;
+        __syncthreads();
+        {
+            const double *tp = Ds + (size_t)j * PGPFA_TILE + w * 64 + lane * 2;
+            double a2 = 0.0;
+#pragma unroll
+            for (int sp = 0; sp < 8; sp++) {
+                const double2 a = *reinterpret_cast<const double2 *>(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
+                const double2 v = *reinterpret_cast<const double2 *>(tmp + sp * 8 + c2);
+                a2 += a.x * v.x + a.y * v.y;
+            }
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+            if ((lane & 3) == 0) z[j * PGPFA_NB + w * 8 + (lane >> 2)] = a2;
+        }
+        __syncthreads();
+    }
+    // ---- backward: L^T x = y   (right-looking over block rows, streaming each block row once)
+    const int colbase = (w >> 2) * 32 + (w & 3) * 8;       // this warp's 8-column group inside a tile
+    const int toff = (w >> 2) * PGPFA_SLAB + (w & 3) * 512 + lane * 2;
+    for (int i = nb - 1; i >= 0; i--) {
+        {
+            const double *tp = Ds + (size_t)i * PGPFA_TILE + toff;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 8; rb++) {
+                const double2 a = *reinterpret_cast<const double2 *>(tp + rb * 64);
+                const double v = z[i * PGPFA_NB + rb * 8 + (lane >> 2)];
+                ax += a.x * v;
+                ay += a.y * v;
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
+            }
+            if (lane < 4) { tmp[colbase + 2 * lane] = ax; tmp[colbase + 2 * lane + 1] = ay; }
+        }
+        __syncthreads();
+        if (tid < PGPFA_NB) z[i * PGPFA_NB + tid] = tmp[tid];
+        const double *row = Ls + ltile(i, 0) * PGPFA_TILE + toff;
+        double dv[8];
+#pragma unroll
+        for (int rb = 0; rb < 8; rb++) dv[rb] = tmp[rb * 8 + (lane >> 2)];
+        for (int k = 0; k < i; k++) {
+            const double *tp = row + (size_t)k * PGPFA_TILE;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 8; rb++) {
+                const double2 a = *reinterpret_cast<const double2 *>(tp + rb * 64);
+                ax += a.x * dv[rb];
+                ay += a.y * dv[rb];
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
+            }
+            if (lane < 4) {
+                z[k * PGPFA_NB + colbase + 2 * lane] -= ax;
+                z[k * PGPFA_NB + colbase + 2 * lane + 1] -= ay;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) out[(size_t)trial * n + i] = scale * z[i];
+}
+
+}  // namespace
+
+int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
+                  int n, int nslots, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    const int nb = pgpfa_nb(n);
+    const size_t smem = (size_t)(nb * PGPFA_NB + PGPFA_NB) * sizeof(double);
+    if (smem > 48 * 1024) {
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    chol_solve_kernel<<<nslots, 256, smem, st>>>(L, Dinv, rhs, out, scale, act, nb, n);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
