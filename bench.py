@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Headline benchmark: EM iterations / second of full-batch Laplace EM (E-step + M-step) on
+1024 trials, q=8 latents, N=100 neurons, T=200 bins (BASELINE.json configs[2]), synthetic data.
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU under torchrun)
+  python bench.py --impl reference [--steps K --warmup W]    the reference algorithm on the host CPU
+
+A step is one EM iteration (E-step + M-step) of one fit; warm-up iterations are the first W
+iterations of the same fit (cold start included), the timed K iterations follow directly, i.e.
+steady-state warm-started EM.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(q=8, N=100, T=200, R=1024, binSize=10, dOffset=-1.0, seed=1)
+METRIC = "EM iters/sec (Laplace E+M, 1024 trials q=8 T=200)"
+
+
+def make_data(w, R=None):
+    from poisson_gpfa_b200 import util
+    R = w["R"] if R is None else R
+    ex = util.simulate(w["seed"], w["q"], w["N"], R, w["T"], binSize=w["binSize"], dOffset=w["dOffset"])
+    np.random.seed(123)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ip = util.initializeParams(w["q"], w["N"], ex)
+    ip = {k: np.ascontiguousarray(np.real(v), dtype=np.float64) for k, v in ip.items()}
+    return ex, ip
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [s.strip() for s in l.split(",")]
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except Exception:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_sample(w, R_cpu, n_iter=1):
+    """The reference algorithm (oracle dense port: same C_big / K_big formulation, same scipy optimisers and
+    options as funs/inference.py + funs/learning.py) on a bounded sample of the same workload."""
+    from oracle import pgpfa_oracle as po
+    ex, ip = make_data(w, R_cpu)
+    ex_o = po.Experiment([{'Y': np.asarray(t['Y'], dtype=np.float64)} for t in ex.data], ex.trialDur, ex.binSize)
+    t0 = time.time()
+    out = po.batch_em_dense(ex_o, ip, n_iter)
+    dt = time.time() - t0
+    return dt / n_iter, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = dict(WORKLOAD)
+    R_cpu = args.cpu_trials
+    times = []
+    for i in range(args.warmup_ref + args.steps):
+        sec, _ = cpu_sample(w, R_cpu, 1)
+        if i >= args.warmup_ref:
+            times.append(sec)
+    sec = float(np.mean(times))
+    value = 1.0 / (sec * w["R"] / R_cpu)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "EM iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": 1e3 / value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: synthetic q=8 N=100 T=200 R=1024 full-batch Laplace EM"},
+            "cpu_baseline": {"value": value, "unit": "EM iters/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "one cold EM iteration (dense C_big formulation, scipy Newton-CG/TNC/BFGS at the "
+                                       "reference's options) on %d of 1024 trials, %.1f s; per-trial cost is exactly "
+                                       "linear in trials (serial loops funs/inference.py:94, funs/learning.py:39), "
+                                       "extrapolated x%d" % (R_cpu, sec, w["R"] // R_cpu)},
+            "e2e": {"value": value, "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    from poisson_gpfa_b200 import _lib, core, dist, inference, learning
+    red = dist.init_from_env()
+    rank, world = red.rank, red.world_size
+    if world == 1:
+        torch.cuda.set_device(0)
+    dev_index = torch.cuda.current_device()
+    w = dict(WORKLOAD)
+    if args.trials:
+        w["R"] = args.trials
+    ex, ip = make_data(w)
+    q, N, T, R = w["q"], w["N"], w["T"], w["R"]
+    n = q * T
+
+    Y_host = np.stack([np.asarray(t['Y'], dtype=np.float64) for t in ex.data])
+    lo, hi = dist.shard_bounds(R, world, rank)
+    trials = core.DeviceTrials(_lib.dev_f64(Y_host[lo:hi]), w["binSize"], red, R_total=R, offset=lo)
+    h = _lib.handle()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def em_iteration(params, x0):
+        est = trials.estep_laplace(params, x0=x0)
+        lik = trials.post_lik(est)
+        C, d, cost, cd_it, _ = trials.mstep_cd(params, est)
+        Psum = trials.pautosum(est)
+        tau, det = trials.mstep_tau(params, Psum)
+        newp = core.DeviceParams(C, d, tau, T, w["binSize"])
+        return newp, est, lik, cd_it, det['nfev']
+
+    params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
+    x0, liks = None, []
+    for _ in range(args.warmup):
+        params, est, lik, _, _ = em_iteration(params, x0)
+        x0 = est.x
+        liks.append(lik)
+
+    # ---------------- timed region: K steady-state EM iterations, device-resident inputs
+    _lib.call("pgpfa_set_profiling", h, 1)
+    sampler = ClockSampler(dev_index)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.pgpfa_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    newton_its, facts, cd_its, tau_evals = [], 0, [], []
+    for _ in range(args.steps):
+        params, est, lik, cd_it, nfev = em_iteration(params, x0)
+        x0 = est.x
+        liks.append(lik)
+        newton_its.append(est.stats["max_newton_iters"]); facts += est.stats["factorizations"]
+        cd_its.append(cd_it); tau_evals.append(nfev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.lib.pgpfa_launch_count() - launches0
+    prof_ms, prof_work, prof_cnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    _lib.call("pgpfa_get_profile", h, ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_work, ctypes.c_void_p),
+              ctypes.cast(prof_cnt, ctypes.c_void_p))
+    _lib.call("pgpfa_set_profiling", h, 0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps / (ms * 1e-3)
+
+    # ---------------- e2e: the same EM iteration through the public API with HOST buffers every step
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    Y_pin = torch.from_numpy(Y_host).pin_memory()
+    host_params = params.to_numpy_dict()
+    modes_host = est.x.cpu().numpy()            # this rank's modes
+    e2e_t = []
+    h2d = d2h = 0
+    for i in range(e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        exp = inference_experiment(Y_pin, w)
+        prev = None
+        if modes_host is not None:
+            full = np.zeros((R, n))
+            full[lo:hi] = modes_host.reshape(hi - lo, n)
+            prev = list(full)
+        infRes, lik_e, optim = inference.laplace(exp, host_params, prevOptimRes=prev, reducer=red)
+        host_params, det = learning.updateParams(host_params, infRes, exp)
+        modes_host = optim.tensor.cpu().numpy()
+        barrier()
+        if i > 0:
+            e2e_t.append(time.perf_counter() - t0)
+        h2d = Y_pin.numel() * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
+        d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8
+    e2e_sec = float(np.mean(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
+    except Exception:
+        pass
+    fp64_peak = float(peaks.get("fp64_roofline_peak_tflops", 35.4))
+    fac_ms, fac_flops, fac_cnt = prof_ms[0], prof_work[0], prof_cnt[0]
+    achieved = fac_flops / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "batched Cholesky (chol_diag_kernel + chol_panel_kernel, DMMA.8x8x4)",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None,
+                "peak_source": "measured cuBLAS DGEMM 8192^3 sustained on this pool (profiles/r01_fp64_peaks.json); "
+                               "MEASURED_PEAKS.json has no FP64 line",
+                "algorithmic_flops_per_launch": fac_flops / max(fac_cnt, 1), "launches": int(fac_cnt),
+                "share_of_step": fac_ms / ms,
+                "other_ms_per_step": {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
+                                      "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
+                                      "factor": fac_ms / args.steps},
+                "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
+                "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
+    cpu = None
+    if not args.skip_cpu and world == 1:
+        sec, _ = cpu_sample(w, args.cpu_trials, 1)
+        v = 1.0 / (sec * R / args.cpu_trials)
+        cpu = {"value": v, "unit": "EM iters/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "one cold EM iteration of the dense reference formulation on %d of %d trials (%.1f s), "
+                         "linear extrapolation in trials" % (args.cpu_trials, R, sec)}
+    line = {"metric": METRIC, "value": value, "unit": "EM iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: synthetic q=8 N=100 T=200 R=%d full-batch Laplace EM, steady-state "
+                                   "(warm-started) iterations" % R,
+                       "trials_per_gpu": hi - lo, "l2": "working set (factor tiles %.1f GB/GPU) >> L2, no flush needed"
+                                                        % ((hi - lo) * 2 * 10.65e6 / 1e9),
+                       "newton_tol": 1e-8},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": 1.0 / e2e_sec, "unit": "EM iters/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "api": "inference.laplace + learning.updateParams with host numpy inputs/outputs each step"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
+                       "tau_evals": tau_evals, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
+    print(json.dumps(line))
+
+
+def inference_experiment(Y_pin, w):
+    """A duck-typed experiment over pinned host counts (re-uploaded by the API on every e2e step)."""
+    from poisson_gpfa_b200 import util
+
+    class _E:
+        pass
+    e = _E()
+    Yn = Y_pin.numpy()
+    e.data = [{'Y': Yn[r]} for r in range(Yn.shape[0])]
+    e.Y_all = Y_pin
+    e.trialDur, e.binSize = w["T"] * w["binSize"], w["binSize"]
+    e.T, e.ydim, e.numTrials = w["T"], w["N"], Yn.shape[0]
+    return e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials", type=int, default=0, help="override the trial count (debug only)")
+    ap.add_argument("--cpu-trials", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup_ref = min(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

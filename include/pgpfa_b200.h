@@ -37,6 +37,12 @@ int pgpfa_create(pgpfa_handle_t *out);                 /* fails with PGPFA_ERR_N
 int pgpfa_destroy(pgpfa_handle_t h);
 const char *pgpfa_error_string(int code);
 const char *pgpfa_last_cuda_error(void);
+long long pgpfa_launch_count(void);                    /* kernels launched by this library so far */
+/* in-stream CUDA-event profiling of the kernel families inside the drivers (bench.py roofline):
+ * slots: 0 batched Cholesky, 1 triangular solves, 2 eval/prior/line-search, 3 triangular inverse,
+ * 4 covariance slices; ms_out/work_out/count_out hold 8 entries each (work = algorithmic flops or bytes) */
+int pgpfa_set_profiling(pgpfa_handle_t h, int on);
+int pgpfa_get_profile(pgpfa_handle_t h, double *ms_out, double *work_out, long long *count_out);
 
 /* ---- (1) GP prior: funs/util.py:599-619 makeK_big, funs/inference.py:82 inv(K_big) ---------- */
 int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double epsNoise, double *K, cudaStream_t stream);

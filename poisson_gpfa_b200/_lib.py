@@ -22,6 +22,9 @@ SIGNATURES = {
     "pgpfa_destroy": (c_int, [c_void_p]),
     "pgpfa_error_string": (ctypes.c_char_p, [c_int]),
     "pgpfa_last_cuda_error": (ctypes.c_char_p, []),
+    "pgpfa_launch_count": (c_ll, []),
+    "pgpfa_set_profiling": (c_int, [c_void_p, c_int]),
+    "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
     "pgpfa_make_K": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P]),
     "pgpfa_make_K_big": (c_int, [P, c_int, c_int, P, P]),
     "pgpfa_make_K_gamma": (c_int, [P, c_int, c_int, c_dbl, P, P, P]),

@@ -5,6 +5,7 @@
 #include "pgpfa_internal.h"
 
 static thread_local char g_last_cuda_error[512] = "";
+unsigned long long g_pgpfa_launches = 0;
 
 void pgpfa_set_last_cuda_error(cudaError_t e, const char *file, int line) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s (%s) at %s:%d", cudaGetErrorName(e),
@@ -15,6 +16,54 @@ void pgpfa_set_last_cuda_error(cudaError_t e, const char *file, int line) {
 extern "C" const char *pgpfa_last_cuda_error(void) { return g_last_cuda_error; }
 
 extern "C" int pgpfa_abi_version(void) { return PGPFA_ABI_VERSION; }
+
+extern "C" long long pgpfa_launch_count(void) { return (long long)g_pgpfa_launches; }
+
+// ---- lightweight in-stream profiling (CUDA events around kernel families inside the drivers) ----
+void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st) {
+    if (!h || !h->profiling) return;
+    PgpfaProfSpan sp;
+    sp.slot = slot;
+    cudaEventCreate(&sp.e0);
+    cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, st);
+    h->open_spans.push_back(sp);
+}
+void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st) {
+    if (!h || !h->profiling || h->open_spans.empty()) return;
+    cudaEventRecord(h->open_spans.back().e1, st);
+    h->spans.push_back(h->open_spans.back());
+    h->open_spans.pop_back();
+}
+void pgpfa_prof_resolve(pgpfa_handle_t h) {   // call after a stream synchronise
+    if (!h) return;
+    for (auto &sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { h->prof_ms[sp.slot] += ms; h->prof_cnt[sp.slot] += 1; }
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    h->spans.clear();
+}
+
+extern "C" int pgpfa_set_profiling(pgpfa_handle_t h, int on) {
+    if (!h) return PGPFA_ERR_ARG;
+    h->profiling = on != 0;
+    for (int i = 0; i < PGPFA_PROF_SLOTS; i++) { h->prof_ms[i] = 0.0; h->prof_cnt[i] = 0; h->prof_work[i] = 0.0; }
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_get_profile(pgpfa_handle_t h, double *ms_out, double *work_out, long long *count_out) {
+    if (!h || !ms_out) return PGPFA_ERR_ARG;
+    cudaDeviceSynchronize();
+    pgpfa_prof_resolve(h);
+    for (int i = 0; i < PGPFA_PROF_SLOTS; i++) {
+        ms_out[i] = h->prof_ms[i];
+        if (work_out) work_out[i] = h->prof_work[i];
+        if (count_out) count_out[i] = h->prof_cnt[i];
+    }
+    return PGPFA_OK;
+}
 
 extern "C" const char *pgpfa_error_string(int code) {
     switch (code) {
@@ -39,6 +88,8 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
     }
     pgpfa_handle_s *h = new pgpfa_handle_s();
     h->pinned = nullptr;
+    h->profiling = false;
+    for (int i = 0; i < PGPFA_PROF_SLOTS; i++) { h->prof_ms[i] = 0.0; h->prof_cnt[i] = 0; h->prof_work[i] = 0.0; }
     PGPFA_CUDA_TRY(cudaGetDevice(&h->device));
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&h->pinned), 256, cudaHostAllocDefault);
     if (e != cudaSuccess) {

@@ -40,7 +40,11 @@ enum {
             return PGPFA_ERR_CUDA;                            \
         }                                                     \
     } while (0)
-#define PGPFA_LAUNCH_CHECK() PGPFA_CUDA_TRY(cudaGetLastError())
+#define PGPFA_LAUNCH_CHECK()                 \
+    do {                                     \
+        g_pgpfa_launches++;                  \
+        PGPFA_CUDA_TRY(cudaGetLastError());  \
+    } while (0)
 #define PGPFA_TRY(expr)          \
     do {                         \
         int _r = (expr);         \
@@ -48,6 +52,7 @@ enum {
     } while (0)
 
 void pgpfa_set_last_cuda_error(cudaError_t e, const char *file, int line);
+extern unsigned long long g_pgpfa_launches;   // kernels launched by this library (bench.py gpu_launches)
 
 static inline int pgpfa_nb(int n) { return (n + PGPFA_NB - 1) / PGPFA_NB; }
 static inline long long pgpfa_ltiles(int nb) { return (long long)nb * (nb + 1) / 2; }

@@ -403,19 +403,30 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         int *act = w.actA, *act_next = w.actB;
         int n_act = cn;
         for (int it = 0; it < max_newton && n_act > 0; it++) {
+            pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
+            pgpfa_prof_end(h, st);
+            pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_FACTOR] += (double)n_act * n * (double)n * n / 3.0;
+            pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
             PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, act, n, n_act, st));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_SOLVE] += (double)n_act * 2.0 * (double)(ltl + nb) * PGPFA_TILE * 8;
+            pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
                                          niter, w.steplen, st));
+            pgpfa_prof_end(h, st);
             compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, act_next, w.cnt);
             PGPFA_LAUNCH_CHECK();
             total_factor_trials += n_act;
             PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
             PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
             n_act = h->pinned[0];
+            pgpfa_prof_resolve(h);
             int *tmp = act; act = act_next; act_next = tmp;
             if (it + 1 > max_it_used) max_it_used = it + 1;
         }
@@ -426,13 +437,21 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, w.actA, cn, q, T, st));
         PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, w.actA, cn, q, N, T, f_out, w.g, w.W, st));
         if (vsm || vsmGP || cov_dense) {
+            pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_FACTOR] += (double)cn * n * (double)n * n / 3.0;
             total_factor_trials += cn;
+            pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);
             PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_TRTRI] += (double)cn * n * (double)n * n / 3.0;
+            pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
             if (vsmGP || cov_dense)
                 PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,
                                         cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
+            pgpfa_prof_end(h, st);
         }
     }
     if (stats_out) {

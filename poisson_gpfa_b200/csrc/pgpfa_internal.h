@@ -28,10 +28,29 @@ int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double
 #include <vector>
 #include "../../include/pgpfa_b200.h"
 
+// profiling slots (pgpfa_get_profile): time in ms, algorithmic work (flops or bytes), span count
+enum {
+    PGPFA_PROF_FACTOR = 0,    // batched Cholesky (diag + panel kernels); work = trial-factorisations * n^3/3 flops
+    PGPFA_PROF_SOLVE = 1,     // triangular solves; work = bytes of factor streamed (2 passes)
+    PGPFA_PROF_EVAL = 2,      // prior mat-vec + fused rates/gradient/W + line search
+    PGPFA_PROF_TRTRI = 3,     // triangular inverse; work = trials * n^3/3 flops
+    PGPFA_PROF_SLICES = 4,    // time-diagonals + selected inverse tiles
+    PGPFA_PROF_SLOTS = 8
+};
+struct PgpfaProfSpan { cudaEvent_t e0, e1; int slot; };
+
 struct pgpfa_handle_s {
     int *pinned;        // small pinned host scratch for device -> host counters
     int device;
+    bool profiling;
+    double prof_ms[PGPFA_PROF_SLOTS];
+    double prof_work[PGPFA_PROF_SLOTS];
+    long long prof_cnt[PGPFA_PROF_SLOTS];
+    std::vector<PgpfaProfSpan> spans, open_spans;
 };
+void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
+void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
+void pgpfa_prof_resolve(pgpfa_handle_t h);
 
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
                         cudaStream_t st);

@@ -1,0 +1,122 @@
+"""Mirror of the hot-path part of the reference's ``funs/util.py`` (same names, arguments, returns).
+
+GP covariance construction runs on the device; vec(C,d) packing, trial sub-sampling and the
+Poisson-PCA initialiser are host-side bookkeeping exactly as in the reference (they feed the hot
+path but are not part of it).
+"""
+import copy
+
+import numpy as np
+import torch
+
+from . import _lib, kernels as kn
+
+
+def makeK_big(params, trialDur, binSize, epsNoise=0.001):
+    """(K_big (qT,qT), K (q,T,T)) — funs/util.py:599-619.  Like the reference it flattens
+    ``params['tau']`` in place (:602)."""
+    params['tau'] = np.ndarray.flatten(np.asarray(params['tau'], dtype=np.float64))
+    T = int(trialDur / binSize)
+    K = kn.make_K(_lib.dev_f64(params['tau']), T, binSize, epsNoise)
+    K_big = kn.make_K_big(K)
+    return K_big.cpu().numpy(), K.cpu().numpy()
+
+
+def makeCd_big(params, T):
+    """(C_big (qT,NT), d_big (NT,)) — funs/util.py:594-597.  Kept for API compatibility only: the
+    rebuilt hot path never materialises C_big.  Pure data movement (a Kronecker
+    product with the identity), done with device indexing."""
+    C = _lib.dev_f64(params['C'])
+    N, q = C.shape
+    C_big = torch.zeros(q, T, N, T, dtype=torch.float64, device="cuda")
+    idx = torch.arange(T, device="cuda")
+    C_big[:, idx, :, idx] = C.T.reshape(1, q, N).expand(T, q, N)
+    d_big = _lib.dev_f64(np.ravel(params['d'])).repeat_interleave(T)
+    return C_big.reshape(q * T, N * T).cpu().numpy(), d_big.cpu().numpy()
+
+
+def CdtoVecCd(C, d):
+    """funs/util.py:560-574: vecCd[j*N+n] = C[n,j], vecCd[q*N+n] = d[n]."""
+    C = np.asarray(C)
+    return np.concatenate([C.T.reshape(-1), np.ravel(d)])
+
+
+def vecCdtoCd(vecCd, xdim, ydim):
+    """funs/util.py:576-592."""
+    m = np.reshape(vecCd, [xdim + 1, ydim]).T
+    return m[:, :xdim], m[:, xdim]
+
+
+def seenTrials(experiment, seenIdx):
+    """funs/util.py:449-457."""
+    idx = np.asarray(seenIdx).flatten()
+    out = copy.copy(experiment)
+    out.data = [experiment.data[i] for i in idx]
+    out.numTrials = len(out.data)
+    return out
+
+
+def subsampleTrials(experiment, batchSize):
+    """funs/util.py:459-473: one ``np.random.choice(numTrials, batchSize, replace=False)`` on the GLOBAL
+    numpy RNG per call (RNG-stream parity with the reference's online EM)."""
+    numTrials = len(experiment.data)
+    batchTrIdx = np.random.choice(numTrials, batchSize, replace=False)
+    out = copy.copy(experiment)
+    out.data = [experiment.data[i] for i in batchTrIdx]
+    out.numTrials = batchSize
+    out.batchTrIdx = batchTrIdx
+    out._pgpfa_parent = experiment      # lets the device layer gather the batch from the resident parent
+    out.__dict__.pop('_pgpfa_dev', None)
+    return out
+
+
+def initializeParams(xdim, ydim, experiment=None):
+    """funs/util.py:505-558 (random, or Poisson-PCA moment matching when an experiment is given)."""
+    if experiment is None:
+        print('Initializing parameters randomly..')
+        return {'C': np.random.rand(ydim, xdim) * 2 - 1,
+                'd': np.random.randn(ydim) * 2 - 2,
+                'tau': np.random.rand(xdim) * 0.5}
+    print('Initializing parameters with Poisson-PCA..')
+    spikes = np.concatenate([np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data], axis=1)
+    meanY = np.mean(spikes, 1) + 1e-10
+    covY = np.cov(spikes)
+    lamb = np.log(np.abs(covY + np.outer(meanY, meanY) - np.diag(meanY))) - np.log(np.outer(meanY, meanY))
+    gamma = np.log(meanY)
+    evals, evecs = np.linalg.eig(lamb)
+    order = np.argsort(evals)[::-1]
+    evecs = evecs[:, order][:, :xdim]
+    return {'C': evecs, 'd': gamma, 'tau': np.random.rand(xdim) * 0.5 + 0.1}
+
+
+class Experiment:
+    """Minimal duck-typed experiment (attributes read by the hot path: funs/engine.py:131-136)."""
+
+    def __init__(self, data, trialDur, binSize, params=None):
+        self.data = data
+        self.trialDur = trialDur
+        self.binSize = binSize
+        self.T = int(trialDur / binSize)
+        self.numTrials = len(data)
+        self.ydim = np.shape(data[0]['Y'])[0]
+        if params is not None:
+            self.params = params
+            self.xdim = np.shape(params['C'])[1]
+
+
+def simulate(seed, xdim, ydim, numTrials, T, binSize=10, dOffset=-1.0, tau=None):
+    """Synthetic Poisson-GPFA data with the reference generator's distributions (funs/util.py:707-750):
+    C ~ U(-0.5,0.5), d ~ -2U(0,1)+dOffset, x_k ~ GP(0,K(tau_k)), y ~ Poisson(exp(Cx+d)).  Sampled per
+    latent through a Cholesky factor (host side; input generation is outside the hot path)."""
+    rng = np.random.RandomState(seed)
+    C = rng.rand(ydim, xdim) - 0.5
+    d = rng.rand(ydim) * (-2) + dOffset
+    tau = np.linspace(0.05, 0.3, xdim) if tau is None else np.asarray(tau, dtype=np.float64)
+    t_ms = np.arange(T) * float(binSize)
+    dif2 = (t_ms[:, None] - t_ms[None, :]) ** 2
+    Lk = np.stack([np.linalg.cholesky(0.999 * np.exp(-0.5 * dif2 / (tk * 1000) ** 2) + 0.001 * np.eye(T)) for tk in tau])
+    data = []
+    for _ in range(numTrials):
+        X = np.einsum('kts,ks->kt', Lk, rng.randn(xdim, T))
+        data.append({'X': X, 'Y': rng.poisson(np.exp(C @ X + d[:, None]))})
+    return Experiment(data, T * binSize, binSize, {'C': C, 'd': d, 'tau': tau.copy()})

@@ -1,0 +1,167 @@
+"""GPU parity tests of the reference-facing API (inference.laplace, learning.updateParams,
+engine.PPGPFAfit) against golden vectors from the unmodified reference and against the oracle.
+
+Parity protocol: function-level parity at identical inputs (1e-10 or better); fixed points
+within 1e-8 of the tightly converged oracle (exact Newton on the reference's own objective, pinned to
+the reference in tests/test_oracle_golden.py); and agreement with the reference's own tightened runs to
+the accuracy scipy's optimisers can attain (mode 5e-7, C/d 2e-6)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import Exp, init_params, load_golden, rel
+from oracle import pgpfa_oracle as po
+
+pytestmark = pytest.mark.gpu
+CASES = [("example_laplace", 2, 20, 50), ("small_q3_laplace", 3, 7, 40)]
+
+
+@pytest.mark.parametrize("name,q,N,T", CASES)
+def test_reference_signature_functions(name, q, N, T):
+    """negLogPosteriorUnNorm{,_grad,_hess}(xbar, ybar, C_big, d_big, K_bigInv, xdim, ydim) and the M-step cost
+    functions, called exactly like the reference, against reference outputs."""
+    from poisson_gpfa_b200 import inference, learning, util
+    g = load_golden(name)
+    ip = init_params(g)
+    ex = Exp(g)
+    K_big, K = util.makeK_big(ip, ex.trialDur, ex.binSize)
+    assert rel(K, g['K0']) <= 1e-15
+    C_big, d_big = util.makeCd_big(ip, T)
+    C_big_o, d_big_o = po.make_Cd_big(ip, T)
+    assert np.array_equal(C_big, C_big_o) and np.array_equal(d_big, d_big_o)
+    K_bigInv = np.linalg.inv(K_big)
+    ybar = g['Y'][0].reshape(-1)
+    assert rel(inference.negLogPosteriorUnNorm(g['fn_x'], ybar, C_big, d_big, K_bigInv, q, N), g['fn_f']) <= 1e-12
+    assert rel(inference.negLogPosteriorUnNorm_grad(g['fn_x'], ybar, C_big, d_big, K_bigInv, q, N), g['fn_g']) <= 1e-10
+    assert rel(inference.negLogPosteriorUnNorm_hess(g['fn_x'], ybar, C_big, d_big, K_bigInv, q, N), g['fn_H']) <= 1e-11
+    infRes = {'post_mean': list(g['it0_post_mean']), 'post_vsm': list(g['it0_post_vsm']),
+              'post_vsmGP': list(g['it0_post_vsmGP'])}
+    assert rel(learning.MStepObservationCost(g['fn_vecCd'], q, N, ex, infRes), g['fn_cd_cost']) <= 1e-12
+    assert rel(learning.MStepObservationCost_grad(g['fn_vecCd'], q, N, ex, infRes), g['fn_cd_grad']) <= 1e-11
+    Lam = -np.eye(q * N + N) / 0.4 ** 2
+    assert rel(learning.MStepObservationCostWithPrior(g['fn_vecCd'], ip, q, N, ex, infRes, Lam), g['fn_cd_cost_prior']) <= 1e-12
+    assert rel(learning.MStepObservationCostWithPrior_grad(g['fn_vecCd'], ip, q, N, ex, infRes, Lam), g['fn_cd_grad_prior']) <= 1e-11
+    pre = learning.makePrecomp(infRes)
+    assert rel(np.stack([p['PautoSum'] for p in pre]), g['fn_PautoSum']) <= 1e-14
+    pp = g['fn_tau_p']
+    assert rel([learning.MStepGPtimescaleCost(pp[k], pre[k], 0.001) for k in range(q)], g['fn_tau_cost']) <= 1e-11
+    assert rel([learning.MStepGPtimescaleCost_grad(pp[k], pre[k], 0.001) for k in range(q)], g['fn_tau_grad']) <= 1e-7
+    assert rel([learning.MStepGPtimescaleCostWithPrior(pp[k], pre[k], 0.001, ex.binSize, ip['tau'][k], 0.5)
+                for k in range(q)], g['fn_tau_cost_prior']) <= 1e-11
+    assert rel([learning.MStepGPtimescaleCostWithPrior_grad(pp[k], pre[k], 0.001, ex.binSize, ip['tau'][k], 0.5)
+                for k in range(q)], g['fn_tau_grad_prior']) <= 1e-7
+
+
+@pytest.mark.parametrize("name,q,N,T", CASES)
+def test_em_iterations_teacher_forced(name, q, N, T):
+    """Each EM iteration started from the reference's own previous parameters / modes."""
+    from poisson_gpfa_b200 import inference, learning
+    g = load_golden(name)
+    ex = Exp(g)
+    ys = list(g['Y'])
+    params = init_params(g)
+    prev = None
+    for it in range(int(g['n_iter'])):
+        infRes, post_lik, optim = inference.laplace(ex, copy.deepcopy(params), prevOptimRes=prev)
+        ir, lik_o, opt_o, _ = po.laplace_struct(ys, copy.deepcopy(params), T, ex.binSize, want_cov=(it == 0))
+        # (a) against the fixed point: north-star tolerance 1e-8
+        assert rel(np.stack(list(infRes['post_mean'])), np.stack(ir['post_mean'])) <= 1e-8
+        assert rel(np.stack(list(infRes['post_vsm'])), np.stack(ir['post_vsm'])) <= 1e-8
+        assert rel(np.stack(list(infRes['post_vsmGP'])), np.stack(ir['post_vsmGP'])) <= 1e-8
+        assert abs(post_lik - lik_o) <= 1e-10 * abs(lik_o)
+        # (b) against the reference's tightened run: limited by scipy Newton-CG's attainable accuracy
+        assert rel(np.stack(list(infRes['post_mean'])), g['it%d_post_mean' % it]) <= 5e-7
+        assert rel(np.stack(list(infRes['post_vsm'])), g['it%d_post_vsm' % it]) <= 1e-7
+        assert rel(np.stack(list(infRes['post_vsmGP'])), g['it%d_post_vsmGP' % it]) <= 1e-7
+        assert abs(post_lik - float(g['it%d_post_lik' % it])) <= 1e-10 * abs(post_lik)
+        if it == 0:
+            assert rel(infRes['post_cov'][0], ir['post_cov'][0]) <= 1e-8
+            assert rel(infRes['post_cov'][0], g['it0_post_cov0']) <= 1e-7
+            assert infRes['post_vsmGP'][0].shape == (T, T, q) and infRes['post_vsm'][0].shape == (T, q, q)
+            assert optim[0].shape == (q * T,)
+        # M-step on the REFERENCE's posterior (plain dict of numpy lists, as the reference API passes it)
+        gold = {'post_mean': list(g['it%d_post_mean' % it]), 'post_vsm': list(g['it%d_post_vsm' % it]),
+                'post_vsmGP': list(g['it%d_post_vsmGP' % it])}
+        newParams, det = learning.updateParams(copy.deepcopy(params), gold, ex, CdOptimMethod='TNC')
+        C_o, d_o, cost_o = po.learn_Cd_newton(params, ys, gold['post_mean'], gold['post_vsm'])
+        assert rel(newParams['C'], C_o) <= 1e-8 and rel(newParams['d'], d_o) <= 1e-8
+        assert abs(det['Cd'] - cost_o) <= 1e-11 * abs(cost_o)
+        assert rel(newParams['C'], g['it%d_new_C' % it]) <= 2e-6 and rel(newParams['d'], g['it%d_new_d' % it]) <= 2e-6
+        grad_at_ours = po.mstep_obs_grad(po.Cd_to_vec(newParams['C'], newParams['d']), q, N, ys, gold)
+        assert np.abs(grad_at_ours).max() <= 1e-10        # stationarity under the reference's gradient formula
+        assert det['Cd'] <= float(g['it%d_cd_cost' % it]) + 1e-12
+        assert rel(newParams['tau'], g['it%d_new_tau' % it]) <= 1e-8
+        # continue from the reference's parameters and modes
+        params = {'C': g['it%d_new_C' % it], 'd': g['it%d_new_d' % it], 'tau': g['it%d_new_tau' % it]}
+        prev = [m.reshape(-1) for m in g['it%d_post_mean' % it]]
+
+
+@pytest.mark.parametrize("name,q,N,T", CASES)
+def test_engine_batch_free_running(name, q, N, T):
+    """PPGPFAfit(EMmode='Batch') end to end vs the oracle's tightly converged EM and the stock reference."""
+    from poisson_gpfa_b200 import engine
+    g = load_golden(name)
+    ex = Exp(g)
+    n_iter = int(g['n_iter'])
+    fit = engine.PPGPFAfit(experiment=ex, initParams=init_params(g), inferenceMethod='laplace', EMmode='Batch',
+                           maxEMiter=n_iter, quiet=True)
+    assert len(fit.paramSeq) == n_iter + 1 and len(fit.posteriorLikelihood) == n_iter
+    ys = list(g['Y'])
+    params, x0s = init_params(g), None
+    for it in range(n_iter):
+        params, lik, x0s, _ = po.em_step_struct(ys, params, T, ex.binSize, x0s)
+        assert abs(fit.posteriorLikelihood[it] - lik) <= 1e-9 * abs(lik)
+        assert rel(fit.paramSeq[it + 1]['C'], params['C']) <= 1e-7
+        assert rel(fit.paramSeq[it + 1]['d'], params['d']) <= 1e-7
+        assert rel(fit.paramSeq[it + 1]['tau'], params['tau']) <= 1e-7
+    # the stock reference (default scipy tolerances) lands within its own optimiser slack of the same point
+    assert rel(fit.optimParams['C'], g['stock_C']) <= 5e-3
+    assert rel(fit.optimParams['tau'], g['stock_tau']) <= 5e-3
+    assert rel(fit.posteriorLikelihood, g['stock_post_lik']) <= 1e-5
+    assert fit.tauSeq.shape == (q, n_iter) and fit.inferenceTime.shape == (n_iter,)
+
+
+def test_engine_online_diag_matches_reference_batches():
+    """Online EM, 'diag' rule: same mini-batches as the reference (global numpy RNG), parameters per iteration."""
+    from poisson_gpfa_b200 import engine
+    g = load_golden("example_online_diag")
+    ex = Exp(g)
+    np.random.seed(int(g['seed']))
+    n_iter = g['batches'].shape[0]
+    fit = engine.PPGPFAfit(experiment=ex, initParams=init_params(g), inferenceMethod='laplace', EMmode='Online',
+                           maxEMiter=n_iter, batchSize=int(g['batchSize']), onlineParamUpdateMethod='diag', quiet=True)
+    assert np.array_equal(np.stack(fit.seenTrialIdx), g['batches'])
+    for it in range(n_iter + 1):
+        # The reference's tau update with prior is ill-defined: MStepGPtimescaleCostWithPrior_grad adds
+        # d(reg)/d(tau) to a d/dp gradient (funs/learning.py:734,769, no chain-rule factor), so cost and
+        # "gradient" disagree and scipy TNC stops somewhere between the zero of that gradient (what we return)
+        # and the minimum of the cost: 1e-6..4e-4 apart on this case.  C, d inherit it through the next E-step.
+        assert rel(fit.paramSeq[it]['C'], g['seq_C'][it]) <= 2e-3
+        assert rel(fit.paramSeq[it]['d'], g['seq_d'][it]) <= 2e-3
+        assert rel(fit.paramSeq[it]['tau'], g['seq_tau'][it]) <= 5e-3
+    assert rel(fit.posteriorLikelihood, g['post_lik']) <= 1e-5
+    # first iteration: C, d do not depend on the tau quirk yet -> optimiser-accuracy agreement
+    assert rel(fit.paramSeq[1]['C'], g['seq_C'][1]) <= 2e-6 and rel(fit.paramSeq[1]['d'], g['seq_d'][1]) <= 2e-6
+    assert len(fit.invPriorCovs) == n_iter + 1
+
+
+def test_config3_shape_small_trial_count():
+    """The north-star shape (q=8, N=100, T=200) on a handful of trials: one EM iteration vs the oracle."""
+    from poisson_gpfa_b200 import inference, learning, util
+    ex = util.simulate(1, 8, 100, 4, 200, binSize=10, dOffset=-1.0)
+    ys = [np.asarray(t['Y'], dtype=np.float64) for t in ex.data]
+    rng = np.random.RandomState(3)
+    params = {'C': ex.params['C'] + 0.05 * rng.randn(100, 8), 'd': ex.params['d'] + 0.05 * rng.randn(100),
+              'tau': ex.params['tau'] * 1.1}
+    infRes, lik, optim = inference.laplace(ex, copy.deepcopy(params))
+    newParams, det = learning.updateParams(copy.deepcopy(params), infRes, ex)
+    p_o, lik_o, _, ir = po.em_step_struct(ys, copy.deepcopy(params), 200, 10)
+    assert rel(np.stack(list(infRes['post_mean'])), np.stack(ir['post_mean'])) <= 1e-8
+    assert rel(np.stack(list(infRes['post_vsm'])), np.stack(ir['post_vsm'])) <= 1e-8
+    assert abs(lik - lik_o) <= 1e-10 * abs(lik_o)
+    assert rel(newParams['C'], p_o['C']) <= 1e-8 and rel(newParams['d'], p_o['d']) <= 1e-8
+    # tau: the stationarity condition is a difference of O(R T) traces through K^-1 (cond ~1e5); its zero is
+    # defined to ~1e-8 relative at best on either side
+    assert rel(newParams['tau'], p_o['tau']) <= 1e-7
