@@ -84,12 +84,16 @@ int pgpfa_hessian_dense(const double *Kinv, const double *W, double diag_scale, 
 long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chunk);
 /* Batched Newton to ||step||_inf <= tol (1+||x||_inf) per trial, then posterior slices at the mode.
  * x: in = start (zeros or warm start, funs/inference.py:99-102), out = mode (post_mean).
- * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[4] = {trial-factorisations, max Newton
- * iterations, trials not converged, chunk size}. */
+ * reuse_factor != 0: the workspace still holds the factors left by the previous call for the SAME trials
+ * (previous EM iteration); they drive cheap stale-factor (chord) iterations before any new factorisation,
+ * with automatic per-trial fall-back to exact Newton.  Same fixed point, fewer factorisations.
+ * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[8] = {trial-factorisations, max Newton
+ * iterations, trials not converged, chunk size, chord iterations, trials that fell back to Newton,
+ * factors kept (1/0), 0}. */
 int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
-                        double *x, int R, int q, int N, int T, double tol, int max_newton, double *f_out, double *vsm,
-                        double *vsmGP, double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
-                        int *stats_out, cudaStream_t stream);
+                        double *x, int R, int q, int N, int T, double tol, int max_newton, int reuse_factor,
+                        double *f_out, double *vsm, double *vsmGP, double *cov_dense, int *niter, int *info,
+                        void *workspace, long long ws_bytes, int *stats_out, cudaStream_t stream);
 
 /* ---- (4) M-step: funs/learning.py:20-309 (+ prior variants :445-534, :681-769) ---------------- */
 /* PautoSum[k][s][t] (+)= sum_r vsmGP[r][k][s][t] + m[r][k][s] m[r][k][t]   funs/learning.py:162-165 */

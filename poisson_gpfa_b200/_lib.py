@@ -44,7 +44,7 @@ SIGNATURES = {
     "pgpfa_laplace_eval": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "pgpfa_hessian_dense": (c_int, [P, P, c_dbl, c_int, c_int, c_int, P, P]),
     "pgpfa_laplace_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
-    "pgpfa_laplace_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int,
+    "pgpfa_laplace_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int,
                                     P, P, P, P, P, P, P, c_ll, P, P]),
     "pgpfa_pautosum": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "pgpfa_mstep_cd_nstats": (c_int, [c_int]),

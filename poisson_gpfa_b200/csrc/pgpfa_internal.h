@@ -23,7 +23,7 @@ int pgpfa_i_timediag(const double *ZT, const int *act, double *vsm, int n, int q
 int pgpfa_i_logdet(const double *L, int n, int nslots, double *out, cudaStream_t st);
 int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, double *out, cudaStream_t st);
 int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
-                  int n, int nslots, cudaStream_t st);
+                  int n, int nslots, cudaStream_t st, int lslot_base = -1);
 
 #include <vector>
 #include "../../include/pgpfa_b200.h"
@@ -59,7 +59,8 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
                          cudaStream_t st);
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
-                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, cudaStream_t st);
+                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
+                       cudaStream_t st);
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);

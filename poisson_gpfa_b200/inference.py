@@ -40,6 +40,18 @@ def _full_counts(experiment):
     return y
 
 
+def upload_counts(experiment):
+    """Re-copy the host spike counts into the resident device buffer (keeps workspaces and kept factors)."""
+    y = experiment.__dict__.get('_pgpfa_y')
+    if y is None:
+        return _full_counts(experiment)
+    if getattr(experiment, 'Y_all', None) is not None:
+        y.copy_(torch.as_tensor(experiment.Y_all), non_blocking=True)
+    else:
+        y.copy_(torch.from_numpy(np.stack([np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data])))
+    return y
+
+
 def device_trials(experiment, reducer=None):
     """This rank's shard of the experiment (contiguous block of trials).  Every rank keeps
     the full count tensor resident (164 MB at the 1024-trial shape) and works on its own block."""
