@@ -82,6 +82,7 @@ struct FactorArgs {
     int nb;
     int step;
     int mode;           // panel kernel: 0 = Cholesky panel, 1 = triangular-inverse row
+    int tile0;          // panel kernel, mode 0: first tile row handled is step + 1 + tile0
 };
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
@@ -126,48 +127,109 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_diag_kernel(Factor
                     if (c <= r) S[r * SLD + c] = mat_elem(a.src, trial, slot, f, i, jj, e) - acc[i][jj][e];
                 }
     }
-    // right-looking unblocked Cholesky of the lower triangle of S
-    int bad = 0;
-    for (int c = 0; c < PGPFA_NB; c++) {
+    // blocked right-looking Cholesky (8x8 sub-blocks) + blocked triangular inverse, all in shared memory
+    double *DI = X + PGPFA_NB * SLD;          // [8][8][8] inverses of the diagonal sub-blocks
+    double *TT = DI + 8 * 64;                 // [7][8][8] scratch for the inverse
+    int *bad_sm = reinterpret_cast<int *>(TT + 7 * 64);
+    if (tid == 0) *bad_sm = 0;
+    for (int b = 0; b < 8; b++) {
         __syncthreads();
-        double piv = S[c * SLD + c];
-        if (!(piv > 0.0)) { if (!bad) bad = j * PGPFA_NB + c + 1; piv = 1.0; }
-        const double inv = 1.0 / piv;
-        const int m = PGPFA_NB - 1 - c;
-        for (int idx = tid; idx < m * m; idx += PGPFA_GEMM_THREADS) {
-            const int rr = idx / m, cc = idx - rr * m;
-            if (cc <= rr) {
-                const int r = c + 1 + rr, c2 = c + 1 + cc;
-                S[r * SLD + c2] -= S[r * SLD + c] * S[c2 * SLD + c] * inv;
+        if (warp == 0) {
+            // 8x8 diagonal sub-block: lane i (mod 8) owns row i in registers, pivots travel by shuffle
+            const int i = lane & 7;
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = (c <= i) ? S[(8 * b + i) * SLD + 8 * b + c] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                double piv = __shfl_sync(0xffffffffu, a[k], k);
+                if (!(piv > 0.0)) { if (lane == 0 && *bad_sm == 0) *bad_sm = j * PGPFA_NB + 8 * b + k + 1; piv = 1.0; }
+                const double dd = sqrt(piv), dinv = 1.0 / dd;
+                a[k] = (i == k) ? dd : ((i > k) ? a[k] * dinv : a[k]);
+#pragma unroll
+                for (int c = k + 1; c < 8; c++) {
+                    const double lck = __shfl_sync(0xffffffffu, a[k], c);
+                    if (i >= c) a[c] -= a[k] * lck;
+                }
+            }
+            // inverse of the sub-block: lane i owns column i of it (forward substitution)
+            double xv[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const double lrr = __shfl_sync(0xffffffffu, a[r], r);
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < r) { const double lrk = __shfl_sync(0xffffffffu, a[k], r); sacc += lrk * xv[k]; }
+                xv[r] = (r < i) ? 0.0 : ((r == i) ? 1.0 / lrr : -sacc / lrr);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) if (c <= i) S[(8 * b + i) * SLD + 8 * b + c] = a[c];
+#pragma unroll
+                for (int r = 0; r < 8; r++) DI[b * 64 + r * 8 + i] = xv[r];
             }
         }
         __syncthreads();
-        const double d = sqrt(piv);
-        if (tid == 0) S[c * SLD + c] = d;
-        for (int r = c + 1 + tid; r < PGPFA_NB; r += PGPFA_GEMM_THREADS) S[r * SLD + c] = S[r * SLD + c] / d;
+        // panel below the sub-block: P = S_panel * Dinv_b^T (one thread per row)
+        {
+            const int r = 8 * (b + 1) + tid;
+            if (r < PGPFA_NB) {
+                double v[8], o[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = S[r * SLD + 8 * b + k];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double acc2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k <= c) acc2 += v[k] * DI[b * 64 + c * 8 + k];
+                    o[c] = acc2;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) S[r * SLD + 8 * b + c] = o[c];
+            }
+        }
+        __syncthreads();
+        // trailing update of the remaining lower triangle: 8x8 blocks (rb >= cb > b), 64 threads per block
+        {
+            const int m = 7 - b;                       // remaining block rows
+            const int nblk = m * (m + 1) / 2;
+            const int half = tid >> 6, e = tid & 63, er = e >> 3, ec = e & 7;
+            for (int bi = half; bi < nblk; bi += 2) {
+                // bi -> (rb, cb) in the lower triangle of an m x m block grid
+                int rb = 0, acc_i = 0;
+                while (acc_i + rb + 1 <= bi) { acc_i += rb + 1; rb++; }
+                const int cb = bi - acc_i;
+                const int r = 8 * (b + 1 + rb) + er, c2 = 8 * (b + 1 + cb) + ec;
+                double sum = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) sum += S[r * SLD + 8 * b + k] * S[c2 * SLD + 8 * b + k];
+                if (c2 <= r) S[r * SLD + c2] -= sum;
+            }
+        }
     }
     __syncthreads();
-    if (bad && tid == 0 && a.info) atomicCAS(&a.info[trial], 0, bad);
-    // X = L^-1 by column-parallel forward substitution (thread c owns column c)
-    if (tid < PGPFA_NB) {
-        const int c = tid;
-        for (int r = 0; r < PGPFA_NB; r++) {
-            double v;
-            if (r < c) v = 0.0;
-            else if (r == c) v = 1.0 / S[c * SLD + c];
-            else {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int k = c;
-                for (; k + 3 < r; k += 4) {
-                    s0 += S[r * SLD + k] * X[k * SLD + c];
-                    s1 += S[r * SLD + k + 1] * X[(k + 1) * SLD + c];
-                    s2 += S[r * SLD + k + 2] * X[(k + 2) * SLD + c];
-                    s3 += S[r * SLD + k + 3] * X[(k + 3) * SLD + c];
-                }
-                for (; k < r; k++) s0 += S[r * SLD + k] * X[k * SLD + c];
-                v = -((s0 + s1) + (s2 + s3)) / S[r * SLD + r];
-            }
-            X[r * SLD + c] = v;
+    if (tid == 0 && *bad_sm && a.info) atomicCAS(&a.info[trial], 0, *bad_sm);
+    // X = L^-1 by block rows: X(b,b) = DI_b ; X(b,j) = -DI_b * sum_{k=j}^{b-1} L(b,k) X(k,j)
+    for (int e = tid; e < PGPFA_NB * PGPFA_NB; e += PGPFA_GEMM_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        X[r * SLD + c] = ((r >> 3) == (c >> 3)) ? DI[(r >> 3) * 64 + (r & 7) * 8 + (c & 7)] : 0.0;
+    }
+    for (int b = 1; b < 8; b++) {
+        __syncthreads();
+        for (int e = tid; e < 64 * b; e += PGPFA_GEMM_THREADS) {
+            const int jb = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+            double sum = 0.0;
+            for (int k = 8 * jb; k < 8 * b; k++) sum += S[(8 * b + rr) * SLD + k] * X[k * SLD + 8 * jb + cc];
+            TT[e] = sum;
+        }
+        __syncthreads();
+        for (int e = tid; e < 64 * b; e += PGPFA_GEMM_THREADS) {
+            const int jb = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+            double sum = 0.0;
+#pragma unroll
+            for (int mm = 0; mm < 8; mm++) if (mm <= rr) sum += DI[b * 64 + rr * 8 + mm] * TT[jb * 64 + mm * 8 + cc];
+            X[(8 * b + rr) * SLD + 8 * jb + cc] = -sum;
         }
     }
     __syncthreads();
@@ -199,7 +261,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(Facto
     double *out;
     int nslab, ti = 0, tj = 0;
     if (a.mode == 0) {
-        const int j = a.step, i = j + 1 + blockIdx.x;
+        const int j = a.step, i = j + 1 + a.tile0 + blockIdx.x;
         A = Ls + ltile(i, 0) * PGPFA_TILE;
         B = Ls + ltile(j, 0) * PGPFA_TILE;
         nslab = 2 * j;
@@ -436,7 +498,7 @@ void launch_timediag(const double *ZT, const int *act, double *vsm, int nb, int 
 // internal host API (used by laplace.cu / mstep.cu / the C-ABI wrappers in api.cu)
 // =============================================================================================
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
-                   cudaStream_t st) {
+                   cudaStream_t st, pgpfa_handle_s *h) {
     if (nslots <= 0) return PGPFA_OK;
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
@@ -445,16 +507,62 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
     a.L = L; a.Dinv = Dinv; a.ZT = ZT; a.act = act; a.info = info;
     a.nb = pgpfa_nb(ms.n);
     a.mode = 0;
-    for (int j = 0; j < a.nb; j++) {
+    a.tile0 = 0;
+    const int nb = a.nb;
+    if (h == nullptr || nb < 4 || nslots < 8) {
+        for (int j = 0; j < nb; j++) {
+            a.step = j;
+            chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+            PGPFA_LAUNCH_CHECK();
+            if (j + 1 < nb) {
+                dim3 grid(nb - 1 - j, nslots);
+                chol_panel_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+                PGPFA_LAUNCH_CHECK();
+            }
+        }
+        return PGPFA_OK;
+    }
+    // Look-ahead schedule (depth 1).  Panel step j is split into its first tile row (j+1, j) and the rest
+    // (i >= j+2).  Critical stream: diag(j) -> first(j); bulk stream: rest(j).  diag(j+1) only needs
+    // first(j) and rest(<= j-1), so the latency-bound 64x64 factor/inverse of the next diagonal tile runs
+    // underneath the tensor-bound rest(j) instead of in front of it.
+    while ((int)h->ev_diag.size() < nb) {
+        cudaEvent_t e1, e2;
+        PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        h->ev_diag.push_back(e1);
+        h->ev_rest.push_back(e2);
+    }
+    cudaStream_t sA = h->s_crit, sB = h->s_bulk;
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_fork, 0));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(sB, h->ev_fork, 0));
+    for (int j = 0; j < nb; j++) {
         a.step = j;
-        chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+        if (j >= 2) PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_rest[j - 2], 0));
+        chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sA>>>(a);
         PGPFA_LAUNCH_CHECK();
-        if (j + 1 < a.nb) {
-            dim3 grid(a.nb - 1 - j, nslots);
-            chol_panel_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+        PGPFA_CUDA_TRY(cudaEventRecord(h->ev_diag[j], sA));
+        if (j + 1 < nb) {
+            if (j >= 1) PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_rest[j - 1], 0));
+            a.tile0 = 0;
+            dim3 g1(1, nslots);
+            chol_panel_kernel<<<g1, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sA>>>(a);
             PGPFA_LAUNCH_CHECK();
         }
+        PGPFA_CUDA_TRY(cudaStreamWaitEvent(sB, h->ev_diag[j], 0));
+        if (j + 2 < nb) {
+            a.tile0 = 1;
+            dim3 g2(nb - 2 - j, nslots);
+            chol_panel_kernel<<<g2, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sB>>>(a);
+            PGPFA_LAUNCH_CHECK();
+        }
+        PGPFA_CUDA_TRY(cudaEventRecord(h->ev_rest[j], sB));
     }
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join_a, sA));
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join_b, sB));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join_a, 0));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join_b, 0));
     return PGPFA_OK;
 }
 
@@ -466,6 +574,7 @@ int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int ns
     a.L = const_cast<double *>(L); a.Dinv = const_cast<double *>(Dinv); a.ZT = ZT; a.act = nullptr; a.info = nullptr;
     a.nb = pgpfa_nb(n);
     a.mode = 1;
+    a.tile0 = 0;
     for (int i = 1; i < a.nb; i++) {
         a.step = i;
         dim3 grid(i, nslots);

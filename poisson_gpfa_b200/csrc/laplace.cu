@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
                 sl * sl * sl / (prev * prev) <= 0.1 * tol * scale)
                 state = 1;
         } else {
-            const double chord_goal = 2e-3;
+            const double chord_goal = 1e-2;
             const double prev = steplen[trial];
             state = (sl <= chord_goal * scale) ? 2 : 0;
             if (state == 0 && chord_it >= 1 && sl > 0.7 * prev) state = 2;
@@ -495,7 +495,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
             pgpfa_prof_end(h, st);
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
-            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st));
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st, h));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_FACTOR] += (double)n_act * n * (double)n * n / 3.0;
             pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
@@ -524,7 +524,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         pgpfa_prof_end(h, st);
         if (vsm || vsmGP || cov_dense || reuse_factor >= 0) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
-            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st));
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_FACTOR] += (double)cn * n * (double)n * n / 3.0;
             total_factor_trials += cn;

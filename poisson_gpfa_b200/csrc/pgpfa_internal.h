@@ -14,8 +14,9 @@ struct PgpfaMatSrc {
     double diag_scale;
 };
 
+struct pgpfa_handle_s;
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
-                   cudaStream_t st);
+                   cudaStream_t st, pgpfa_handle_s *h = nullptr);
 int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st);
 int pgpfa_i_lauum(const double *ZT, const int2 *pairs, int npairs, const int *act, double *vsmGP, double *dense, int n,
                   int q, int T, int nslots, cudaStream_t st);
@@ -47,6 +48,10 @@ struct pgpfa_handle_s {
     double prof_work[PGPFA_PROF_SLOTS];
     long long prof_cnt[PGPFA_PROF_SLOTS];
     std::vector<PgpfaProfSpan> spans, open_spans;
+    // look-ahead factorisation: critical-path stream (diag + first panel tile, high priority) and bulk stream
+    cudaStream_t s_crit, s_bulk;
+    std::vector<cudaEvent_t> ev_diag, ev_rest;
+    cudaEvent_t ev_fork, ev_join_a, ev_join_b;
 };
 void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
