@@ -116,7 +116,21 @@ def run_reference(args):
 def run_ours(args):
     import torch
     from poisson_gpfa_b200 import _lib, core, dist, inference, learning
-    red = dist.init_from_env()
+    # keep stdout clean for the single JSON line: NCCL's banner goes to stderr
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        red = dist.init_from_env()
+        if red.world_size > 1:
+            red.sum_scalar(1.0)            # forces communicator creation inside the redirected region
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     rank, world = red.rank, red.world_size
     if world == 1:
         torch.cuda.set_device(0)
@@ -187,14 +201,14 @@ def run_ours(args):
     value = args.steps / (ms * 1e-3)
 
     # ---------------- e2e: the same EM iteration through the public API with HOST buffers every step
-    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_steps = max(1, min(args.e2e_steps, args.steps)) if not args.profile_mode else 0
     Y_pin = torch.from_numpy(Y_host).pin_memory()
     host_params = params.to_numpy_dict()
     modes_host = est.x.cpu().numpy()            # this rank's modes
     e2e_t = []
     h2d = d2h = 0
     exp = inference_experiment(Y_pin, w)
-    for i in range(e2e_steps + 1):
+    for i in range(e2e_steps + 1 if e2e_steps else 0):
         barrier()
         t0 = time.perf_counter()
         inference.upload_counts(exp)                       # H2D of this step's inputs (pinned -> HBM)
@@ -211,13 +225,16 @@ def run_ours(args):
             e2e_t.append(time.perf_counter() - t0)
         h2d = Y_pin.numel() * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
         d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8
-    e2e_sec = float(np.mean(e2e_t))
+    e2e_sec = float(np.mean(e2e_t)) if e2e_t else float("nan")
     if world > 1:
         t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_sec = float(t.item())
 
     if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
         return
     peaks = {}
     try:
@@ -240,7 +257,7 @@ def run_ours(args):
                 "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
                 "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
     cpu = None
-    if not args.skip_cpu and world == 1:
+    if not args.skip_cpu and not args.profile_mode and world == 1:
         sec, _ = cpu_sample(w, args.cpu_trials, 1)
         v = 1.0 / (sec * R / args.cpu_trials)
         cpu = {"value": v, "unit": "EM iters/s", "cores": os.cpu_count(), "kind": "port",
@@ -262,6 +279,10 @@ def run_ours(args):
             "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
                        "tau_evals": tau_evals, "chord_iters_per_step": chord_its, "chord_fallback_trials": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
     print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def inference_experiment(Y_pin, w):
@@ -289,6 +310,7 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="timed loop only (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.warmup_ref = min(args.warmup, 1)
