@@ -95,6 +95,29 @@ int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, cons
                         double *f_out, double *vsm, double *vsmGP, double *cov_dense, int *niter, int *info,
                         void *workspace, long long ws_bytes, int *stats_out, cudaStream_t stream);
 
+/* ---- (3) dual variational E-step: funs/inference.py:188-432 ------------------------------------ */
+long long pgpfa_dualvi_workspace_bytes(int R, int q, int T, int chunk);
+/* dualProblem / dualProblem_grad / VIPostMean / VIPostCov at a given lambda (R,N,T) for every trial:
+ * D[r], grad (R,N,T), mean (R,q,T), vsm (R,T,q,q), optional dense covariance.  grad needs vsm. */
+int pgpfa_dualvi_eval(pgpfa_handle_t h, const double *lam, const double *y, const double *C, const double *d,
+                      const double *K, const double *Kinv, int R, int q, int N, int T, double *D, double *grad,
+                      double *mean, double *vsm, double *cov_dense, int *info, void *workspace, long long ws_bytes,
+                      cudaStream_t stream);
+/* the dual optimum for every trial (stationary point of D; the reference approaches it with L-BFGS-B).
+ * x (R,q,T), s (R,N,T) in/out: zeros (cold) or from pgpfa_dualvi_init_from_lambda (warm start).
+ * stats_out[4] = {trial-factorisations, sweeps, trials not converged, chunk} */
+int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *K,
+                       const double *Kinv, double *x, double *s, int R, int q, int N, int T, double tol, int max_iter,
+                       double *lam, double *mean, double *D, double *f_out, double *vsm, double *vsmGP,
+                       double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes, int *stats_out,
+                       cudaStream_t stream);
+/* W[r][k*q+l][t] = sum_n C[n,k] C[n,l] lambda[r][n][t]  (scratch: R*q*T + 2R doubles) */
+int pgpfa_rate_blocks(const double *lam, const double *C, int R, int q, int N, int T, double *W, double *scratch,
+                      cudaStream_t stream);
+int pgpfa_dualvi_init_from_lambda(const double *lam, const double *y, const double *C, const double *d, const double *K,
+                                  int R, int q, int N, int T, double *x, double *s, void *workspace, long long ws_bytes,
+                                  cudaStream_t stream);
+
 /* ---- (4) M-step: funs/learning.py:20-309 (+ prior variants :445-534, :681-769) ---------------- */
 /* PautoSum[k][s][t] (+)= sum_r vsmGP[r][k][s][t] + m[r][k][s] m[r][k][t]   funs/learning.py:162-165 */
 int pgpfa_pautosum(const double *vsmGP, const double *post_mean, int R, int q, int T, int accumulate, double *P,

@@ -106,6 +106,43 @@ def online_case(ref, name, ds, ip, n_iter, batchSize, method):
     print(name, 'written')
 
 
+def vi_case(ref, name, ds, ip, q, N, T):
+    """Dual variational E-step: function values at a random lambda and the reference's tightened optimum
+    (both the bounded-lambda and the log-lambda variants), first E-step only."""
+    out = {'Y': stackY(ds), 'binSize': ds.binSize, 'trialDur': ds.trialDur,
+           'init_C': ip['C'], 'init_d': ip['d'], 'init_tau': ip['tau']}
+    params = copy.deepcopy(ip)
+    Kb, K = ref.util.makeK_big(params, ds.trialDur, ds.binSize)
+    Cb, db = ref.util.makeCd_big(params, T)
+    Kinv = np.linalg.inv(Kb)
+    rng = np.random.RandomState(11)
+    lam = np.exp(0.4 * rng.randn(N * T))
+    yb = out['Y'][0].reshape(-1)
+    out['fn_lam'] = lam
+    out['fn_D'] = ref.inference.dualProblem(lam, yb, Cb, Kb, Kinv, db)
+    out['fn_grad'] = ref.inference.dualProblem_grad(lam, yb, Cb, Kb, Kinv, db)
+    out['fn_Drho'] = ref.inference.dualProblemRho(np.log(lam), yb, Cb, Kb, Kinv, db)
+    out['fn_gradrho'] = ref.inference.dualProblemRho_grad(np.log(lam), yb, Cb, Kb, Kinv, db)
+    cov, prec = ref.inference.VIPostCov(Kinv, Cb, lam)
+    out['fn_cov'], out['fn_prec'] = cov, prec
+    out['fn_mean'] = ref.inference.VIPostMean(Kb, Cb, yb, lam)
+    for tag, loglam in (('lam', False), ('rho', True)):
+        with rh.tight_tolerances(), rh.quiet():
+            infRes, nll, vlb, opt = ref.inference.dualVariational(ds, copy.deepcopy(ip), optimizeLogLambda=loglam)
+        out[tag + '_opt'] = np.stack(opt)
+        out[tag + '_post_mean'] = np.stack(infRes['post_mean'])
+        out[tag + '_post_vsm'] = np.stack(infRes['post_vsm'])
+        out[tag + '_post_vsmGP'] = np.stack(infRes['post_vsmGP'])
+        out[tag + '_post_cov0'] = infRes['post_cov'][0]
+        out[tag + '_post_lik'] = nll
+        out[tag + '_vlb'] = vlb
+        # gradient of the dual at the reference's own optimum: how far scipy's L-BFGS-B stops from stationarity
+        lam_star = np.exp(opt[0]) if loglam else opt[0]
+        out[tag + '_grad_at_opt0'] = ref.inference.dualProblem_grad(lam_star, yb, Cb, Kb, Kinv, db)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'written')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rh.load_reference()
@@ -124,6 +161,14 @@ def main():
                                fixTau=True, fixedTau=np.linspace(0.04, 0.15, 3))
         ip2 = ref.util.initializeParams(3, 7, ds2)
     em_case(ref, 'small_q3_laplace', ds2, ip2, 2, 3, 7, 40)
+    # variational: q=2, N=8, T=20, 3 trials (each reference gradient forms an NT x NT matrix)
+    if 'vi' in sys.argv or len(sys.argv) == 1:
+        np.random.seed(9)
+        with rh.quiet():
+            ds3 = ref.util.dataset(seed=31, xdim=2, ydim=8, numTrials=3, trialDur=200, binSize=10, dOffset=0.5,
+                                   fixTau=True, fixedTau=np.linspace(0.05, 0.12, 2))
+            ip3 = ref.util.initializeParams(2, 8, ds3)
+        vi_case(ref, 'small_vi', ds3, ip3, 2, 8, 20)
 
 
 if __name__ == "__main__":

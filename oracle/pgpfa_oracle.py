@@ -293,6 +293,47 @@ def dual_struct(lam, y, C, d, K, Kinv, want_grad=True):
     return D, g, cov
 
 
+def dual_fixed_point_struct(y, C, d, K, Kinv, tol=1e-12, maxit=1000):
+    """The unique stationary point of the dual (funs/inference.py:196-219): log lam = C m + d + s,
+    m = -K C_big (lam - y), s[n,t] = 0.5 c_n^T Sigma_tt c_n with Sigma = VIPostCov(lam).  Solved by the coupled
+    iteration (Newton step on m with the jittered precision, refresh of s).  Returns a dict."""
+    q, T = K.shape[0], K.shape[1]
+    N = C.shape[0]
+    m = np.zeros((q, T))
+    s = np.zeros((N, T))
+    for it in range(maxit):
+        lam = np.exp(C @ m + d[:, None] + s)
+        g = C.T @ (lam - y) + np.einsum('kts,ks->kt', Kinv, m)
+        P = assemble_H(Kinv, np.einsum('nk,nl,nt->tkl', C, C, lam), diag_jitter=1e-6)
+        cov = np.linalg.inv(P)
+        step = -(cov @ g.ravel()).reshape(q, T)
+        m = m + step
+        vsm = np.stack([cov[t::T, t::T] for t in range(T)])
+        s_new = 0.5 * np.einsum('nk,tkl,nl->nt', C, vsm, C)
+        ds = np.abs(s_new - s).max()
+        s = s_new
+        if np.abs(step).max() <= tol * (1 + np.abs(m).max()) and ds <= tol * (1 + np.abs(s).max()):
+            break
+    lam = np.exp(C @ m + d[:, None] + s)
+    D, grad, cov = dual_struct(lam, y, C, d, K, Kinv)
+    mean = -np.einsum('kts,ks->kt', K, C.T @ (lam - y))
+    vsmGP, vsm = slice_cov(cov, q, T)
+    return {'lam': lam, 'mean': mean, 'cov': cov, 'vsm': vsm, 'vsmGP': vsmGP, 'D': D, 'grad': grad, 'iters': it + 1,
+            'post_lik_term': nlp_struct(mean, y, C, d, Kinv)}
+
+
+def dual_variational_struct(ys, params, T, binSize):
+    """Structured, tightly converged dual variational E-step (list of per-trial dicts + the reference's scalars)."""
+    C = np.asarray(params['C'], dtype=np.float64)
+    d = np.ravel(np.asarray(params['d'], dtype=np.float64))
+    K = make_K(params['tau'], T, binSize)
+    Kinv = np.stack([np.linalg.inv(K[k]) for k in range(C.shape[1])])
+    out = [dual_fixed_point_struct(y, C, d, K, Kinv) for y in ys]
+    post_lik = -np.mean([o['post_lik_term'] for o in out])
+    lower = np.mean([o['D'] for o in out])
+    return out, post_lik, lower
+
+
 def dense_dual_variational(experiment, params, optimizeLogLambda=False, prevOptimRes=None,
                            factr=None, pgtol=None):
     """funs/inference.py:259-432 (L-BFGS-B over lambda >= 1e-10 from 0.5, factr=1e7; or over rho)."""

@@ -46,6 +46,12 @@ SIGNATURES = {
     "pgpfa_laplace_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "pgpfa_laplace_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int,
                                     P, P, P, P, P, P, P, c_ll, P, P]),
+    "pgpfa_dualvi_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
+    "pgpfa_dualvi_eval": (c_int, [c_void_p, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_ll, P]),
+    "pgpfa_dualvi_solve": (c_int, [c_void_p, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int,
+                                   P, P, P, P, P, P, P, P, P, P, c_ll, P, P]),
+    "pgpfa_rate_blocks": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "pgpfa_dualvi_init_from_lambda": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_ll, P]),
     "pgpfa_pautosum": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "pgpfa_mstep_cd_nstats": (c_int, [c_int]),
     "pgpfa_mstep_cd_workspace_bytes": (c_ll, [c_int, c_int]),

@@ -105,6 +105,21 @@ class DeviceTrials:
                                      % int((res.info != 0).sum()))
         return EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
 
+    def estep_variational(self, params, lam0=None, tol=1e-10, max_iter=300, want_vsmGP=True):
+        """Dual variational E-step (funs/inference.py:259-432): the stationary point of the dual for every
+        trial of the shard.  Returns (EStepResult with the VARIATIONAL mean/covariance slices, lam (R,N,T),
+        dual values (R))."""
+        res = kn.dualvi_solve(self.y, params.C, params.d, params.K, params.Kinv, lam0=lam0, tol=tol,
+                              max_iter=max_iter, want_vsmGP=want_vsmGP)
+        if int(res.info.abs().max()) != 0:
+            raise FloatingPointError("variational posterior precision not positive definite")
+        if res.rc != 0:
+            raise RuntimeError("dual variational fixed point: %d trial(s) not converged in %d sweeps"
+                               % (res.stats["not_converged"], max_iter))
+        est = EStepResult(res.mean, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
+        est.lam, est.dual = res.lam, res.D
+        return est
+
     def post_lik(self, est):
         """-mean_r L(x_r*) over ALL trials (funs/inference.py:175,183)."""
         return -self.reducer.sum_scalar(float(est.f.sum())) / self.R_total

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restri
 template <int Q>
 __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restrict__ x, const double *__restrict__ Kx,
                                                            const double *__restrict__ y, const double *__restrict__ C,
-                                                           const double *__restrict__ d, const int *act, int N, int T,
+                                                           const double *__restrict__ d, const double *__restrict__ off,
+                                                           const int *act, int N, int T,
                                                            double *__restrict__ f, double *__restrict__ g,
                                                            double *__restrict__ W) {
     extern __shared__ double sm[];
@@ -75,11 +76,13 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
 #pragma unroll
         for (int i = 0; i < Q * (Q + 1) / 2; i++) w[i] = 0.0;
         const double *yp = y + (size_t)trial * N * T + t;
+        const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
         for (int n = 0; n < N; n++) {
             double h = ds[n];
 #pragma unroll
             for (int k = 0; k < Q; k++) h += Cs[n * Q + k] * xk[k];
-            const double lam = exp(h);
+            // variational path: rates carry the extra log-offset s[n,t] = 0.5 c_n^T Sigma_tt c_n
+            const double lam = op ? exp(h + op[(size_t)n * T]) : exp(h);
             const double yy = yp[(size_t)n * T];
             fl += lam - yy * h;
             const double r = lam - yy;
@@ -116,8 +119,9 @@ template <int Q>
 __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     double *__restrict__ x, const double *__restrict__ dx, const double *__restrict__ Kx, const double *__restrict__ Kd,
     const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
-    const double *__restrict__ d, const int *act, int N, int T, double tol, double *__restrict__ fcur,
-    int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen, int chord_it) {
+    const double *__restrict__ d, const double *__restrict__ off, const int *act, int N, int T, double tol,
+    double *__restrict__ fcur, int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen,
+    int chord_it) {
     extern __shared__ double sm[];
     double *Cs = sm;
     double *ds = sm + N * Q;
@@ -151,12 +155,13 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
 #pragma unroll
             for (int k = 0; k < Q; k++) { xk[k] = x[base + (size_t)k * T + t]; dk[k] = dx[base + (size_t)k * T + t]; }
             const double *yp = y + (size_t)trial * N * T + t;
+            const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
             for (int n = 0; n < N; n++) {
                 double h = ds[n], dh = 0.0;
 #pragma unroll
                 for (int k = 0; k < Q; k++) { h += Cs[n * Q + k] * xk[k]; dh += Cs[n * Q + k] * dk[k]; }
                 const double ha = h + alpha * dh;
-                fl += exp(ha) - yp[(size_t)n * T] * ha;
+                fl += (op ? exp(ha + op[(size_t)n * T]) : exp(ha)) - yp[(size_t)n * T] * ha;
             }
         }
         fl = block_sum(fl, red);
@@ -276,24 +281,24 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
 }
 
 template <int Q>
-int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const int *act,
-                int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st) {
+int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const double *off,
+                const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, act, N, T, f, g, W);
+    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
 
 template <int Q>
 int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
-                      const double *C, const double *d, const int *act, int nslots, int N, int T, double tol,
+                      const double *C, const double *d, const double *off, const int *act, int nslots, int N, int T, double tol,
                       double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, act, N, T, tol, fcur, conv, niter, steplen, chord_it);
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -314,10 +319,10 @@ int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const 
 
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st) {
+                         cudaStream_t st, const double *off) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, act, nslots, N, T, f, g, W, st);
+#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, off, act, nslots, N, T, f, g, W, st);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -327,10 +332,10 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st) {
+                       cudaStream_t st, const double *off) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st);
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }

@@ -61,11 +61,11 @@ int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const 
                         cudaStream_t st);
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st);
+                         cudaStream_t st, const double *off = nullptr);
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st);
+                       cudaStream_t st, const double *off = nullptr);
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);

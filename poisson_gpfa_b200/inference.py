@@ -211,3 +211,115 @@ def laplace(experiment, params, prevOptimRes=None, returnOptimRes=True, verbose=
     if returnOptimRes:
         return infRes, post_lik, _TrialView(est.x, lambda a: a.reshape(-1))
     return infRes, post_lik
+
+
+# ----------------------------------------------------------------------------------------------
+# Dual variational inference
+# ----------------------------------------------------------------------------------------------
+def _infer_T(C_big):
+    """T from the Kronecker structure C_big = kron(C, I_T)^T (funs/util.py:595)."""
+    C_big = np.asarray(C_big)
+    rows, cols = C_big.shape
+    g = np.gcd(rows, cols)
+    for T in sorted({t for t in range(1, g + 1) if g % t == 0}, reverse=True):
+        q, N = rows // T, cols // T
+        blk = C_big.reshape(q, T, N, T)
+        diag = np.einsum('ktnt->knt', blk)
+        if np.count_nonzero(blk) == np.count_nonzero(diag) and np.all(diag == diag[:, :, :1]):
+            return T
+    raise ValueError("C_big is not of the form kron(C, eye(T)).T")
+
+
+def _unpack_vi(C_big, K_big=None, K_bigInv=None, d_big=None):
+    T = _infer_T(C_big)
+    C_big = np.asarray(C_big)
+    q, N = C_big.shape[0] // T, C_big.shape[1] // T
+    C = C_big[::T, ::T].T.copy()
+    blocks = lambda M: np.stack([np.asarray(M)[k * T:(k + 1) * T, k * T:(k + 1) * T] for k in range(q)])
+    K = blocks(K_big) if K_big is not None else None
+    Kinv = blocks(K_bigInv) if K_bigInv is not None else None
+    d = np.asarray(d_big)[::T].copy() if d_big is not None else np.zeros(N)
+    return C, d, K, Kinv, q, N, T
+
+
+def VIPostCov(K_bigInv, C_big, lamb):
+    """(postCovariance, postPrecision) — funs/inference.py:188-191 (relative 1e-6 diagonal jitter before inverting)."""
+    C, d, _, Kinv, q, N, T = _unpack_vi(C_big, K_bigInv=K_bigInv)
+    lam = _f64(np.asarray(lamb, dtype=np.float64).reshape(1, N, T))
+    Kd = _f64(Kinv)
+    K = kn.spd_inverse(Kd)[0]
+    _, _, _, _, cov = kn.dualvi_eval(lam, torch.zeros_like(lam), _f64(C), _f64(d), K, Kd, want_grad=False, want_cov=True)
+    return cov[0].cpu().numpy(), kn.hessian_dense(Kd, kn.rate_blocks(lam, _f64(C)))[0].cpu().numpy()
+
+
+def VIPostMean(K_big, C_big, y_bar, lamb):
+    """-K_big C_big (lamb - y)  — funs/inference.py:193-194."""
+    C, d, K, _, q, N, T = _unpack_vi(C_big, K_big=K_big)
+    lam = _f64(np.asarray(lamb, dtype=np.float64).reshape(1, N, T))
+    y = _f64(np.asarray(y_bar, dtype=np.float64).reshape(1, N, T))
+    Kd = _f64(K)
+    Kinv = kn.spd_inverse(Kd)[0]
+    _, _, mean, _, _ = kn.dualvi_eval(lam, y, _f64(C), _f64(d), Kd, Kinv, want_grad=False)
+    return mean.reshape(-1).cpu().numpy()
+
+
+def _dual_eval(lamb, ybar, C_big, K_big, K_bigInv, d_big):
+    C, d, K, Kinv, q, N, T = _unpack_vi(C_big, K_big, K_bigInv, d_big)
+    lam = _f64(np.asarray(lamb, dtype=np.float64).reshape(1, N, T))
+    y = _f64(np.asarray(ybar, dtype=np.float64).reshape(1, N, T))
+    D, grad, _, _, _ = kn.dualvi_eval(lam, y, _f64(C), _f64(d), _f64(K), _f64(Kinv))
+    return float(D[0]), grad.reshape(-1).cpu().numpy()
+
+
+def dualProblem(lamb, ybar, C_big, K_big, K_bigInv, d_big):
+    """funs/inference.py:196-213."""
+    return _dual_eval(lamb, ybar, C_big, K_big, K_bigInv, d_big)[0]
+
+
+def dualProblem_grad(lamb, ybar, C_big, K_big, K_bigInv, d_big):
+    """funs/inference.py:215-219."""
+    return _dual_eval(lamb, ybar, C_big, K_big, K_bigInv, d_big)[1]
+
+
+def dualProblemRho(rho, ybar, C_big, K_big, K_bigInv, d_big):
+    """funs/inference.py:222-244."""
+    return _dual_eval(np.exp(rho), ybar, C_big, K_big, K_bigInv, d_big)[0]
+
+
+def dualProblemRho_grad(rho, ybar, C_big, K_big, K_bigInv, d_big):
+    """funs/inference.py:246-256."""
+    return _dual_eval(np.exp(rho), ybar, C_big, K_big, K_bigInv, d_big)[1] * np.exp(rho)
+
+
+def dualVariational(experiment, params, optimizeLogLambda=False, prevOptimRes=None, returnOptimRes=True, verbose=False,
+                    tol=1e-10, reducer=None):
+    """varInfRes, -post_lik, var_lowerBound[, varOptimRes] — funs/inference.py:259-432.
+
+    The reference runs L-BFGS-B on the dual per trial (bounded in lambda, or unbounded in rho = log lambda when
+    ``optimizeLogLambda``); both variants have the same unique optimum, which is computed here directly as the
+    stationary point of the dual (see csrc/dualvi.cu).  ``varOptimRes`` holds lambda* (or rho*) per trial."""
+    trials = device_trials(experiment, reducer)
+    T = trials.T
+    p = device_params(params, T, experiment.binSize)
+    params['tau'] = np.ndarray.flatten(np.asarray(params['tau'], dtype=np.float64))
+    lam0 = None
+    if prevOptimRes is not None:
+        if isinstance(prevOptimRes, _TrialView) and prevOptimRes.tensor.shape[0] == trials.R:
+            lam0 = prevOptimRes.tensor.reshape(trials.R, trials.N, T)
+        else:
+            sel = range(trials.offset, trials.offset + trials.R) if len(prevOptimRes) == trials.R_total else range(trials.R)
+            lam0 = _f64(np.stack([np.asarray(prevOptimRes[i], dtype=np.float64).reshape(trials.N, T) for i in sel]))
+        if optimizeLogLambda:
+            lam0 = torch.exp(lam0)
+        lam0 = lam0.contiguous()
+    est = trials.estep_variational(p, lam0=lam0, tol=tol)
+    if verbose:
+        print('dual variational inference: %d trials, %d sweeps' % (trials.R, est.stats['sweeps']))
+
+    infRes = InfRes(est, diag_scale=1.0 + 1e-6, W_fn=lambda r: kn.rate_blocks(est.lam[r:r + 1].contiguous(), p.C))
+    post_lik = trials.post_lik(est)
+    lower = trials.reducer.sum_scalar(float(est.dual.sum())) / trials.R_total
+    if returnOptimRes:
+        opt = torch.log(est.lam) if optimizeLogLambda else est.lam
+        return infRes, post_lik, lower, _TrialView(opt.reshape(trials.R, -1))
+    return infRes, post_lik, lower

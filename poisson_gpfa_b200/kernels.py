@@ -181,6 +181,66 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
     return res
 
 
+def dualvi_eval(lam, y, C, d, K, Kinv, want_grad=True, want_cov=False):
+    """dualProblem / dualProblem_grad / VIPostMean / VIPostCov slices at lambda (R,N,T) — funs/inference.py:188-219."""
+    R, N, T = y.shape
+    q = C.shape[1]
+    D, mean, vsm = empty(R), empty(R, q, T), empty(R, T, q, q)
+    grad = empty(R, N, T) if want_grad else None
+    cov = empty(R, q * T, q * T) if want_cov else None
+    info = empty(R, dtype=torch.int32)
+    nbytes = _lib.lib.pgpfa_dualvi_workspace_bytes(R, q, T, R)
+    ws = workspace(nbytes)
+    call("pgpfa_dualvi_eval", handle(), ptr(lam), ptr(y), ptr(C), ptr(d), ptr(K), ptr(Kinv), R, q, N, T, ptr(D),
+         ptr(grad), ptr(mean), ptr(vsm), ptr(cov), ptr(info), ptr(ws), nbytes, stream())
+    return D, grad, mean, vsm, cov
+
+
+def rate_blocks(lam, C):
+    """W (R, q*q, T) with W[r,k*q+l,t] = sum_n C[n,k] C[n,l] lam[r,n,t]."""
+    R, N, T = lam.shape
+    q = C.shape[1]
+    W = empty(R, q * q, T)
+    scratch = empty(R * q * T + 2 * R)
+    call("pgpfa_rate_blocks", ptr(lam), ptr(C), R, q, N, T, ptr(W), ptr(scratch), stream())
+    return W
+
+
+class DualVIResult:
+    __slots__ = ("x", "s", "lam", "mean", "D", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc")
+
+
+def dualvi_solve(y, C, d, K, Kinv, lam0=None, tol=1e-10, max_iter=200, want_vsmGP=True, want_cov=False, ws=None):
+    """Fixed point of the dual problem for all trials (pgpfa_dualvi_solve)."""
+    R, N, T = y.shape
+    q = C.shape[1]
+    res = DualVIResult()
+    res.x = torch.zeros(R, q, T, dtype=torch.float64, device="cuda")
+    res.s = torch.zeros(R, N, T, dtype=torch.float64, device="cuda")
+    nbytes = _lib.lib.pgpfa_dualvi_workspace_bytes(R, q, T, R)
+    if ws is None:
+        free, _ = torch.cuda.mem_get_info()
+        budget = int(free * 0.8)
+        if nbytes > budget:
+            nbytes = max(budget, _lib.lib.pgpfa_dualvi_workspace_bytes(R, q, T, 1))
+        ws = workspace(nbytes)
+    if lam0 is not None:
+        call("pgpfa_dualvi_init_from_lambda", ptr(lam0), ptr(y), ptr(C), ptr(d), ptr(K), R, q, N, T, ptr(res.x),
+             ptr(res.s), ptr(ws), ws.numel(), stream())
+    res.lam, res.mean, res.D, res.f = empty(R, N, T), empty(R, q, T), empty(R), empty(R)
+    res.vsm = empty(R, T, q, q)
+    res.vsmGP = empty(R, q, T, T) if want_vsmGP else None
+    res.cov = empty(R, q * T, q * T) if want_cov else None
+    res.niter, res.info = empty(R, dtype=torch.int32), empty(R, dtype=torch.int32)
+    stats = (ctypes.c_int * 4)()
+    res.rc = call("pgpfa_dualvi_solve", handle(), ptr(y), ptr(C), ptr(d), ptr(K), ptr(Kinv), ptr(res.x), ptr(res.s),
+                  R, q, N, T, float(tol), int(max_iter), ptr(res.lam), ptr(res.mean), ptr(res.D), ptr(res.f),
+                  ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov), ptr(res.niter), ptr(res.info), ptr(ws), ws.numel(),
+                  ctypes.cast(stats, ctypes.c_void_p), stream(), allow=(_lib.ERR_NOT_CONVERGED,))
+    res.stats = {"factorizations": stats[0], "sweeps": stats[1], "not_converged": stats[2], "chunk": stats[3]}
+    return res
+
+
 def pautosum(vsmGP, post_mean, out=None, accumulate=False):
     R, q, T, _ = vsmGP.shape
     P = out if out is not None else empty(q, T, T)

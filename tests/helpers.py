@@ -10,6 +10,8 @@ def rel(a, b):
         import torch
         if isinstance(a, torch.Tensor):
             a = a.detach().cpu().numpy()
+        if isinstance(b, torch.Tensor):
+            b = b.detach().cpu().numpy()
     except ImportError:
         pass
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

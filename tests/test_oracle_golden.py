@@ -149,3 +149,31 @@ def test_product_path_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_oracle_dual_variational_matches_reference_golden():
+    """Dual problem: function values at a random lambda, and the stationary point vs the reference's tightened
+    L-BFGS-B runs (bounded-lambda and log-lambda variants share one optimum)."""
+    g = load_golden("small_vi")
+    q, N, T = 2, 8, 20
+    ip = init_params(g)
+    K = po.make_K(ip['tau'], T, float(g['binSize']))
+    Kinv = np.stack([np.linalg.inv(K[k]) for k in range(q)])
+    lam = g['fn_lam'].reshape(N, T)
+    D, grad, cov = po.dual_struct(lam, g['Y'][0], ip['C'], ip['d'], K, Kinv)
+    assert rel(D, g['fn_D']) <= 1e-12 and rel(D, g['fn_Drho']) <= 1e-12
+    assert rel(grad.ravel(), g['fn_grad']) <= 1e-10
+    assert rel((grad * lam).ravel(), g['fn_gradrho']) <= 1e-10
+    assert rel(cov, g['fn_cov']) <= 1e-10
+    assert rel(-np.einsum('kts,ks->kt', K, ip['C'].T @ (lam - g['Y'][0])).ravel(), g['fn_mean']) <= 1e-12
+    out, post_lik, lower = po.dual_variational_struct(list(g['Y']), ip, T, float(g['binSize']))
+    assert max(np.abs(o['grad']).max() for o in out) <= 1e-10            # stationary under the reference's gradient
+    assert np.abs(g['lam_grad_at_opt0']).max() >= 1e-8                    # ... where the reference itself is not
+    for tag in ('lam', 'rho'):
+        lam_ref = g[tag + '_opt'] if tag == 'lam' else np.exp(g[tag + '_opt'])
+        # scipy L-BFGS-B (factr=10, pgtol=1e-12) stops with |grad| ~ 1e-6: agreement to its attainable accuracy
+        assert rel(np.stack([o['lam'].ravel() for o in out]), lam_ref) <= 2e-6
+        assert rel(np.stack([o['mean'] for o in out]), g[tag + '_post_mean']) <= 2e-6
+        assert rel(out[0]['cov'], g[tag + '_post_cov0']) <= 1e-6
+        assert rel(lower, g[tag + '_vlb']) <= 1e-12
+        assert rel(post_lik, g[tag + '_post_lik']) <= 1e-8
