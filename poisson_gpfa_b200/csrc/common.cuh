@@ -17,10 +17,15 @@
 #define PGPFA_NB 64
 #define PGPFA_TILE 4096          // doubles per tile
 #define PGPFA_SLAB 2048          // doubles per 64x32 k-slab
-#define PGPFA_STAGES 3
+#ifndef PGPFA_STAGES
+#define PGPFA_STAGES 2
+#endif
 #define PGPFA_GEMM_THREADS 128
-// dynamic shared memory of the tile-GEMM kernels: 3 stages x (A slab + B slab) + barriers
-#define PGPFA_GEMM_SMEM (PGPFA_STAGES * 2 * PGPFA_SLAB * 8 + 64)
+#define PGPFA_GEMM_CTAS_PER_SM 3
+// dynamic shared memory of the tile-GEMM kernels: the staging area (PGPFA_STAGES x (A slab + B slab), re-used
+// by the 64x64 diagonal factorisation which needs 74,248 bytes) followed by the mbarriers; 3 CTAs per SM
+#define PGPFA_BAR_OFF 74304
+#define PGPFA_GEMM_SMEM (PGPFA_BAR_OFF + 64)
 
 enum {
     PGPFA_OK = 0,
@@ -123,7 +128,7 @@ struct GemmPipe {
 
 __device__ __forceinline__ void pipe_setup(GemmPipe &p, unsigned char *smem_raw) {
     p.stages = reinterpret_cast<double *>(smem_raw);
-    p.full = reinterpret_cast<uint64_t *>(smem_raw + PGPFA_STAGES * 2 * PGPFA_SLAB * 8);
+    p.full = reinterpret_cast<uint64_t *>(smem_raw + PGPFA_BAR_OFF);
     p.it = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < PGPFA_STAGES; s++) mbar_init(&p.full[s], 1);

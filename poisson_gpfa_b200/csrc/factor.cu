@@ -83,6 +83,8 @@ struct FactorArgs {
     int step;
     int mode;           // panel kernel: 0 = Cholesky panel, 1 = triangular-inverse row
     int tile0;          // panel kernel, mode 0: first tile row handled is step + 1 + tile0
+    int nslots, ntiles; // panel kernel, mode 0: 1-D grid decode (ntiles tile rows per slot)
+    int fuse;           // panel kernel, mode 0: first-tile CTAs also factor diagonal tile step+1
 };
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
@@ -96,22 +98,13 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
 // Diagonal-tile kernel: SYRK update + 64x64 Cholesky + 64x64 triangular inverse (in shared memory)
 // ---------------------------------------------------------------------------------------------
 #define SLD 65
-__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_diag_kernel(FactorArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int slot = blockIdx.x;
-    const int trial = a.act ? a.act[slot] : slot;
-    const int j = a.step;
+// acc holds sum_k L(j,k) L(j,k)^T for the diagonal tile j of this slot: form S = A(j,j) - acc in shared
+// memory, factor it, invert the factor, and write L(j,j), Dinv_j and (optionally) ZT(j,j).
+// Must be entered by all threads with every earlier use of the shared staging area finished (__syncthreads).
+__device__ __forceinline__ void diag_epilogue(const FactorArgs &a, unsigned char *smem_raw, double (&acc)[4][4][2],
+                                              int trial, int slot, int j, double *Ls) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
-    double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
-
-    GemmPipe pipe;
-    pipe_setup(pipe, smem_raw);
-    double acc[4][4][2];
-    zero_acc(acc);
-    const double *Arow = Ls + ltile(j, 0) * PGPFA_TILE;
-    gemm_slabs<true>(acc, pipe, Arow, Arow, 2 * j);
-
     double *S = reinterpret_cast<double *>(smem_raw);      // [64][65]
     double *X = S + PGPFA_NB * SLD;                        // [64][65]
     {
@@ -245,12 +238,41 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_diag_kernel(Factor
     }
 }
 
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) chol_diag_kernel(FactorArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int slot = blockIdx.x;
+    const int trial = a.act ? a.act[slot] : slot;
+    const int j = a.step;
+    const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
+    double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
+    GemmPipe pipe;
+    pipe_setup(pipe, smem_raw);
+    double acc[4][4][2];
+    zero_acc(acc);
+    const double *Arow = Ls + ltile(j, 0) * PGPFA_TILE;
+    gemm_slabs<true>(acc, pipe, Arow, Arow, 2 * j);
+    diag_epilogue(a, smem_raw, acc, trial, slot, j, Ls);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Panel kernel: out = (init - sum_k A_k B_k^T) * D^T   (Cholesky panel tile or inverse-row tile)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(FactorArgs a) {
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) chol_panel_kernel(FactorArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int slot = blockIdx.y;
+    // mode 0 (Cholesky panel of step j): 1-D slot-major grid (a slot's CTAs are neighbours and share the L(j,:)
+    // operand in L2).  The CTA of tile row j+1 goes on, when a.fuse is set, to factor diagonal tile j+1 (which
+    // only waits for this very tile); these long-running CTAs are spread evenly through the launch so that the
+    // second resident CTA of each SM keeps the tensor pipe busy meanwhile.
+    // mode 1 (triangular inverse, row i): 2-D grid (tile, slot).
+    int slot, tile;
+    if (a.mode == 0) {
+        const int b = blockIdx.x;
+        slot = b / a.ntiles;
+        tile = b - slot * a.ntiles + a.tile0;
+    } else {
+        slot = blockIdx.y;
+        tile = blockIdx.x;
+    }
     const int trial = a.act ? a.act[slot] : slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(Facto
     double *out;
     int nslab, ti = 0, tj = 0;
     if (a.mode == 0) {
-        const int j = a.step, i = j + 1 + a.tile0 + blockIdx.x;
+        const int j = a.step, i = j + 1 + tile;
         A = Ls + ltile(i, 0) * PGPFA_TILE;
         B = Ls + ltile(j, 0) * PGPFA_TILE;
         nslab = 2 * j;
@@ -269,7 +291,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(Facto
         out = Ls + ltile(i, j) * PGPFA_TILE;
         ti = i; tj = j;
     } else {
-        const int i = a.step, j = blockIdx.x;
+        const int i = a.step, j = tile;
         A = Zs + utile(j, j, a.nb) * PGPFA_TILE;
         B = Ls + ltile(i, j) * PGPFA_TILE;
         nslab = 2 * (i - j);
@@ -331,6 +353,35 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) chol_panel_kernel(Facto
             v.y = acc[i][jj][1];
             O2[frag_slot2(wm, wn, i, jj, lane)] = v;
         }
+    if (a.mode != 0 || !a.fuse || tile != 0) return;
+    // ---- fused look-ahead: this CTA just produced L(j+1, j), the last tile diagonal step j+1 was waiting for.
+    // Keep it in shared memory (B halves of stages 0/1, untouched by the single-operand pipeline), run the SYRK
+    // over the earlier tiles of block row j+1 from global memory, add the k = j term from shared memory, and
+    // factor / invert diagonal tile j+1 while the other CTAs of this launch finish panel j.
+    const int jn = a.step + 1;
+    __syncthreads();                                   // everyone done reading St / Dt
+    {
+        double2 *N0 = reinterpret_cast<double2 *>(pipe.stages + PGPFA_SLAB);                // slab 0 of L(j+1,j)
+        double2 *N1 = reinterpret_cast<double2 *>(pipe.stages + PGPFA_TILE + PGPFA_SLAB);   // slab 1
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                double2 v;
+                v.x = acc[i][jj][0];
+                v.y = acc[i][jj][1];
+                // frag_slot2 = wn*1024 + jj*256 + (wm*4+i)*32 + lane (double2 units); wn selects the slab
+                (wn == 0 ? N0 : N1)[jj * 256 + (wm * 4 + i) * 32 + lane] = v;
+            }
+    }
+    __syncthreads();
+    zero_acc(acc);
+    const double *Arow = Ls + ltile(jn, 0) * PGPFA_TILE;
+    gemm_slabs<true>(acc, pipe, Arow, Arow, 2 * a.step);
+    slab_mma(acc, pipe.stages + PGPFA_SLAB, pipe.stages + PGPFA_SLAB, wm, wn, lane);
+    slab_mma(acc, pipe.stages + PGPFA_TILE + PGPFA_SLAB, pipe.stages + PGPFA_TILE + PGPFA_SLAB, wm, wn, lane);
+    __syncthreads();
+    diag_epilogue(a, smem_raw, acc, trial, slot, jn, Ls);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,7 +396,7 @@ struct LauumArgs {
     int nb, n, q, T;
 };
 
-__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, 2) lauum_tiles_kernel(LauumArgs a) {
+__global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) lauum_tiles_kernel(LauumArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int slot = blockIdx.y;
     const int trial = a.act ? a.act[slot] : slot;
@@ -499,6 +550,7 @@ void launch_timediag(const double *ZT, const int *act, double *vsm, int nb, int 
 // =============================================================================================
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
                    cudaStream_t st, pgpfa_handle_s *h) {
+    (void)h;
     if (nslots <= 0) return PGPFA_OK;
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
@@ -508,61 +560,21 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
     a.nb = pgpfa_nb(ms.n);
     a.mode = 0;
     a.tile0 = 0;
+    a.nslots = nslots;
+    a.fuse = 1;
     const int nb = a.nb;
-    if (h == nullptr || nb < 4 || nslots < 8) {
-        for (int j = 0; j < nb; j++) {
-            a.step = j;
-            chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
-            PGPFA_LAUNCH_CHECK();
-            if (j + 1 < nb) {
-                dim3 grid(nb - 1 - j, nslots);
-                chol_panel_kernel<<<grid, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
-                PGPFA_LAUNCH_CHECK();
-            }
-        }
-        return PGPFA_OK;
-    }
-    // Look-ahead schedule (depth 1).  Panel step j is split into its first tile row (j+1, j) and the rest
-    // (i >= j+2).  Critical stream: diag(j) -> first(j); bulk stream: rest(j).  diag(j+1) only needs
-    // first(j) and rest(<= j-1), so the latency-bound 64x64 factor/inverse of the next diagonal tile runs
-    // underneath the tensor-bound rest(j) instead of in front of it.
-    while ((int)h->ev_diag.size() < nb) {
-        cudaEvent_t e1, e2;
-        PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-        PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        h->ev_diag.push_back(e1);
-        h->ev_rest.push_back(e2);
-    }
-    cudaStream_t sA = h->s_crit, sB = h->s_bulk;
-    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_fork, 0));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(sB, h->ev_fork, 0));
-    for (int j = 0; j < nb; j++) {
+    // diag(0), then one launch per panel step j: its first-tile CTAs also factor diagonal tile j+1 (fused
+    // look-ahead), so the latency-bound 64x64 factor/inverse never runs in front of the tensor-bound panel.
+    a.step = 0;
+    chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
+    PGPFA_LAUNCH_CHECK();
+    for (int j = 0; j + 1 < nb; j++) {
         a.step = j;
-        if (j >= 2) PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_rest[j - 2], 0));
-        chol_diag_kernel<<<nslots, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sA>>>(a);
+        a.ntiles = nb - 1 - j;
+        const long long blocks = (long long)nslots * a.ntiles;
+        chol_panel_kernel<<<(unsigned)blocks, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, st>>>(a);
         PGPFA_LAUNCH_CHECK();
-        PGPFA_CUDA_TRY(cudaEventRecord(h->ev_diag[j], sA));
-        if (j + 1 < nb) {
-            if (j >= 1) PGPFA_CUDA_TRY(cudaStreamWaitEvent(sA, h->ev_rest[j - 1], 0));
-            a.tile0 = 0;
-            dim3 g1(1, nslots);
-            chol_panel_kernel<<<g1, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sA>>>(a);
-            PGPFA_LAUNCH_CHECK();
-        }
-        PGPFA_CUDA_TRY(cudaStreamWaitEvent(sB, h->ev_diag[j], 0));
-        if (j + 2 < nb) {
-            a.tile0 = 1;
-            dim3 g2(nb - 2 - j, nslots);
-            chol_panel_kernel<<<g2, PGPFA_GEMM_THREADS, PGPFA_GEMM_SMEM, sB>>>(a);
-            PGPFA_LAUNCH_CHECK();
-        }
-        PGPFA_CUDA_TRY(cudaEventRecord(h->ev_rest[j], sB));
     }
-    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join_a, sA));
-    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join_b, sB));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join_a, 0));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join_b, 0));
     return PGPFA_OK;
 }
 
@@ -575,6 +587,7 @@ int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int ns
     a.nb = pgpfa_nb(n);
     a.mode = 1;
     a.tile0 = 0;
+    a.nslots = nslots; a.ntiles = 0; a.fuse = 0;
     for (int i = 1; i < a.nb; i++) {
         a.step = i;
         dim3 grid(i, nslots);
