@@ -128,8 +128,11 @@ long long pgpfa_mstep_cd_workspace_bytes(int q, int N);
  * MStepObservationCost at theta: stats[s][n] */
 int pgpfa_mstep_cd_stats(const double *y, const double *post_mean, const double *vsm, const double *theta, int R, int q,
                          int N, int T, double *stats, void *workspace, long long ws_bytes, cudaStream_t stream);
-/* one accept/reject + Newton-step update per neuron; see poisson_gpfa_b200/learning.py */
-int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *theta0, double *theta_cur,
+/* one accept/reject + Newton-step update per neuron; see poisson_gpfa_b200/learning.py.
+ * prior: 0.5*prior_w*|theta-theta0|^2, or (prior_mat != NULL) 0.5*(theta-theta0)^T M_n (theta-theta0) with
+ * per-neuron packed-upper (q+1)x(q+1) blocks prior_mat[b][n] */
+int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *prior_mat,
+                          const double *theta0, double *theta_cur,
                           double *theta_try, double *fcur, double *step, double *alpha, double *slope, int *done,
                           int first, double tol, int N, int q, int *n_open, cudaStream_t stream);
 long long pgpfa_tau_eval_workspace_bytes(int q, int T);

@@ -102,6 +102,10 @@ def online_case(ref, name, ds, ip, n_iter, batchSize, method):
     out['seq_tau'] = np.stack([np.ravel(p['tau']) for p in fit.paramSeq])
     out['post_lik'] = np.array(fit.posteriorLikelihood)
     out['seed'] = 2024
+    if method in ('hess', 'diag'):
+        out['invPriorCov_last'] = fit.invPriorCovs[-1]
+    if method == 'grad':
+        out['cumHess_last'] = fit.cumHess[-1]
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print(name, 'written')
 
@@ -154,6 +158,8 @@ def main():
         ip = ref.util.initializeParams(2, 20, ds)
     em_case(ref, 'example_laplace', ds, ip, 3, 2, 20, 50)
     online_case(ref, 'example_online_diag', ds, ip, 4, 3, 'diag')
+    online_case(ref, 'example_online_hess', ds, ip, 3, 3, 'hess')
+    online_case(ref, 'example_online_grad', ds, ip, 3, 3, 'grad')
     # small ragged-ish shape: q=3, N=7 (few neurons), T=40, tile-unaligned n=120
     np.random.seed(5)
     with rh.quiet():

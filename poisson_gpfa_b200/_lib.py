@@ -56,7 +56,7 @@ SIGNATURES = {
     "pgpfa_mstep_cd_nstats": (c_int, [c_int]),
     "pgpfa_mstep_cd_workspace_bytes": (c_ll, [c_int, c_int]),
     "pgpfa_mstep_cd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_ll, P]),
-    "pgpfa_mstep_cd_update": (c_int, [P, c_dbl, c_dbl, P, P, P, P, P, P, P, P, c_int, c_dbl, c_int, c_int, P, P]),
+    "pgpfa_mstep_cd_update": (c_int, [P, c_dbl, c_dbl, P, P, P, P, P, P, P, P, P, c_int, c_dbl, c_int, c_int, P, P]),
     "pgpfa_tau_eval_workspace_bytes": (c_ll, [c_int, c_int]),
     "pgpfa_tau_eval": (c_int, [P, P, c_dbl, c_int, c_int, c_dbl, c_dbl, P, c_dbl, P, P, P, c_ll, P]),
 }

@@ -125,7 +125,8 @@ class DeviceTrials:
         return -self.reducer.sum_scalar(float(est.f.sum())) / self.R_total
 
     # ------------------------------------------------------------------ M-step C,d
-    def mstep_cd(self, params, est, prior_w=0.0, tol=1e-10, max_iter=100, one_step=False, step_size=1.0):
+    def mstep_cd(self, params, est, prior_w=0.0, tol=1e-10, max_iter=100, one_step=False, step_size=1.0,
+                 prior_mat=None):
         """Per-neuron damped Newton on MStepObservationCost (+ 0.5*prior_w*|theta-theta_old|^2).
         Returns (C, d, cost, iterations).  `one_step`: a single (scaled) Newton step from the old
         parameters, the 'grad' online rule of funs/learning.py:884-891 with the analytic Hessian."""
@@ -147,13 +148,14 @@ class DeviceTrials:
             stats = self.reducer.sum_tensor(stats)
             if one_step:
                 hess = stats
-                call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(theta0), ptr(th_cur), ptr(th_try),
-                     ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open), stream())
+                call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
+                     ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open),
+                     stream())
                 th_cur = theta0 + step_size * step
                 break
-            call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(theta0), ptr(th_cur), ptr(th_try),
-                 ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol), N, q,
-                 ptr(n_open), stream())
+            call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
+                 ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol),
+                 N, q, ptr(n_open), stream())
             if int(n_open.item()) == 0:
                 break
         cost = float(fcur.sum())

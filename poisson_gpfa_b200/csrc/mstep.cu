@@ -109,7 +109,7 @@ __global__ void mstep_cd_reduce_kernel(const double *__restrict__ partial, int n
 // per-neuron accept/reject and next Newton step.  State arrays are (N) or (N, q+1).
 template <int Q>
 __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double invR, double pw,
-                                       const double *__restrict__ theta0, double *__restrict__ theta_cur,
+                                       const double *__restrict__ pmat, const double *__restrict__ theta0, double *__restrict__ theta_cur,
                                        double *__restrict__ theta_try, double *__restrict__ fcur,
                                        double *__restrict__ step, double *__restrict__ alpha,
                                        double *__restrict__ slope, int *__restrict__ done, int first, double tol, int N,
@@ -118,15 +118,34 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     if (done[n]) return;
-    double tt[P], t0[P];
+    // prior: 0.5 pw |theta - theta0|^2 ('useDiag'), or 0.5 (theta-theta0)^T M_n (theta-theta0) with a per-neuron
+    // (q+1)x(q+1) matrix M_n (packed upper, pmat[b*N+n]) for the accumulated-Hessian rule ('useHessian')
+    double tt[P], t0[P], dl0[P], Md[P];
     double pen = 0.0;
 #pragma unroll
     for (int k = 0; k < P; k++) {
         tt[k] = theta_try[(size_t)n * P + k];
         t0[k] = theta0[(size_t)n * P + k];
-        pen += (tt[k] - t0[k]) * (tt[k] - t0[k]);
+        dl0[k] = tt[k] - t0[k];
+        Md[k] = pw * dl0[k];
     }
-    const double ftry = stats[n] * invR + 0.5 * pw * pen;
+    if (pmat) {
+        int idx = 0;
+#pragma unroll
+        for (int k = 0; k < P; k++) Md[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+            for (int l = k; l < P; l++) {
+                const double m = pmat[(size_t)idx * N + n];
+                Md[k] += m * dl0[l];
+                if (l != k) Md[l] += m * dl0[k];
+                idx++;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < P; k++) pen += dl0[k] * Md[k];
+    const double ftry = stats[n] * invR + 0.5 * pen;
     bool accept = first != 0;
     if (!accept) {
         const double f0 = fcur[n], sl = slope[n], al = alpha[n];
@@ -145,14 +164,15 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
     // accepted: gradient / Hessian at theta_try, Cholesky solve of the (q+1) system
     double g[P], H[P][P];
 #pragma unroll
-    for (int k = 0; k < P; k++) g[k] = stats[(size_t)(1 + k) * N + n] * invR + pw * (tt[k] - t0[k]);
+    for (int k = 0; k < P; k++) g[k] = stats[(size_t)(1 + k) * N + n] * invR + Md[k];
     {
         int idx = 1 + P;
 #pragma unroll
         for (int k = 0; k < P; k++)
 #pragma unroll
             for (int l = k; l < P; l++) {
-                const double v = stats[(size_t)idx * N + n] * invR + ((k == l) ? pw : 0.0);
+                const double v = stats[(size_t)idx * N + n] * invR +
+                                 (pmat ? pmat[(size_t)(idx - 1 - P) * N + n] : ((k == l) ? pw : 0.0));
                 H[k][l] = v;
                 H[l][k] = v;
                 idx++;
@@ -329,7 +349,8 @@ extern "C" int pgpfa_mstep_cd_stats(const double *y, const double *m, const doub
     return PGPFA_OK;
 }
 
-extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *theta0,
+extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *prior_mat,
+                                     const double *theta0,
                                      double *theta_cur, double *theta_try, double *fcur, double *step, double *alpha,
                                      double *slope, int *done, int first, double tol, int N, int q, int *n_open,
                                      cudaStream_t st) {
@@ -338,7 +359,7 @@ extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double p
     PGPFA_CUDA_TRY(cudaMemsetAsync(n_open, 0, sizeof(int), st));
     const int blocks = (N + 63) / 64;
     switch (q) {
-#define CASE_Q(QQ) case QQ: mstep_cd_update_kernel<QQ><<<blocks, 64, 0, st>>>(stats, inv_R, prior_w, theta0, theta_cur, theta_try, fcur, step, alpha, slope, done, first, tol, N, n_open); break;
+#define CASE_Q(QQ) case QQ: mstep_cd_update_kernel<QQ><<<blocks, 64, 0, st>>>(stats, inv_R, prior_w, prior_mat, theta0, theta_cur, theta_try, fcur, step, alpha, slope, done, first, tol, N, n_open); break;
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
         default: return PGPFA_ERR_ARG;

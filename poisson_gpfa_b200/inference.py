@@ -28,12 +28,12 @@ def _full_counts(experiment):
     if y is not None and y.shape[0] == len(experiment.data):
         return y
     parent = experiment.__dict__.get('_pgpfa_parent')
-    if getattr(experiment, 'Y_all', None) is not None:
-        # optional fast path: all counts as one (R,N,T) array / pinned tensor instead of per-trial arrays
-        y = torch.as_tensor(experiment.Y_all).to(device="cuda", dtype=torch.float64, non_blocking=True).contiguous()
-    elif parent is not None and hasattr(experiment, 'batchTrIdx'):
+    if parent is not None and hasattr(experiment, 'batchTrIdx'):
         idx = torch.as_tensor(np.asarray(experiment.batchTrIdx), device="cuda", dtype=torch.long)
         y = _full_counts(parent).index_select(0, idx).contiguous()
+    elif getattr(experiment, 'Y_all', None) is not None:
+        # optional fast path: all counts as one (R,N,T) array / pinned tensor instead of per-trial arrays
+        y = torch.as_tensor(experiment.Y_all).to(device="cuda", dtype=torch.float64, non_blocking=True).contiguous()
     else:
         y = _f64(np.stack([np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data]))
     experiment.__dict__['_pgpfa_y'] = y

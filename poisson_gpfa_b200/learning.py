@@ -100,8 +100,25 @@ def learnLTparamsWithPrior(oldParams, infRes, experiment, CdOptimMethod, regular
         invPriorCov = -np.diag(np.ones(q * N + N)) / (regularizer_stepsize_Cd ** 2)
         C, d, cost, it, _ = trials.mstep_cd(p, est, prior_w=pw, tol=tol)
     elif covOpts == 'useHessian':
-        raise NotImplementedError("covOpts='useHessian' (online 'hess' rule) is scheduled after the 'diag' rule "
-                                  "(SURVEY.md §8f-1)")
+        # reference: invPriorCov = -J, J = finite-difference Jacobian at the old parameters of the prior-cost gradient
+        # = H_base(theta_old) - prevInvPriorCov  (funs/learning.py:545-549).  H_base is block diagonal over neurons;
+        # the per-neuron blocks of prevInvPriorCov are used (the reference's own matrices are block diagonal up to FD noise).
+        P = q + 1
+        pos = (np.arange(P)[:, None] * N + np.arange(N)[None, :])            # vec index of theta[n,k]: pos[k,n]
+        prev = np.asarray(prevInvPriorCov, dtype=np.float64)
+        prev_blocks = np.stack([prev[np.ix_(pos[:, n], pos[:, n])] for n in range(N)])          # (N,P,P)
+        _, _, stats = trials.cd_cost_grad(p.theta, est)
+        st = stats.cpu().numpy() / trials.R_total
+        iu = np.triu_indices(P)
+        Hb = np.zeros((N, P, P))
+        Hb[:, iu[0], iu[1]] = st[1 + P:].T
+        Hb[:, iu[1], iu[0]] = st[1 + P:].T
+        lam_blocks = prev_blocks - Hb
+        pmat = _f64(np.ascontiguousarray((-lam_blocks)[:, iu[0], iu[1]].T))                      # (P(P+1)/2, N)
+        C, d, cost, it, _ = trials.mstep_cd(p, est, prior_mat=pmat, tol=tol)
+        invPriorCov = np.zeros((q * N + N, q * N + N))
+        for n in range(N):
+            invPriorCov[np.ix_(pos[:, n], pos[:, n])] = lam_blocks[n]
     else:
         raise ValueError("covOpts must be 'useDiag' or 'useHessian'")
     if verbose:

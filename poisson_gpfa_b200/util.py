@@ -66,7 +66,8 @@ def subsampleTrials(experiment, batchSize):
     out.numTrials = batchSize
     out.batchTrIdx = batchTrIdx
     out._pgpfa_parent = experiment      # lets the device layer gather the batch from the resident parent
-    out.__dict__.pop('_pgpfa_dev', None)
+    for key in ('_pgpfa_dev', '_pgpfa_y', 'Y_all'):
+        out.__dict__.pop(key, None)
     return out
 
 

