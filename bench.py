@@ -184,7 +184,7 @@ def run_ours(args):
         liks.append(lik)
         newton_its.append(est.stats["max_newton_iters"]); facts += est.stats["factorizations"]
         cd_its.append(cd_it); tau_evals.append(nfev)
-        chord_its.append(est.stats["chord_iters"]); fallback.append(est.stats["chord_fallback_trials"])
+        chord_its.append(est.stats["chord_iters"]); fallback.append(est.stats["fresh_chord_sweeps"])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -277,7 +277,7 @@ def run_ours(args):
                     "api": "inference.laplace + learning.updateParams with host numpy inputs/outputs each step"},
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
-                       "tau_evals": tau_evals, "chord_iters_per_step": chord_its, "chord_fallback_trials": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
+                       "tau_evals": tau_evals, "chord_iters_per_step": chord_its, "fresh_factor_sweeps_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:

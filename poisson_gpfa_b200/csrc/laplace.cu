@@ -182,27 +182,34 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
         const double sl = alpha * dmax;
         // state: 0 keep iterating, 1 converged, 2 stale-factor (chord) iteration contracts too slowly ->
         // hand the trial to the exact-Newton loop
-        // mode < 0: exact Newton, iteration index -mode-1.  Quadratic convergence: with c ~ sl_k / sl_{k-1}^2
-        // the error after this step is ~ c sl_k^2 = sl_k^3 / sl_{k-1}^2; stop as soon as that is below tol
-        // (the posterior pass that follows re-factorises at the new point and applies one more Newton step).
-        // mode >= 0: stale-factor (chord) iteration `mode`; it only has to bring the trial into Newton's
-        // fast regime: stop when the step is below chord_goal, or when it contracts too slowly.
+        // chord_it encodes the kind of step that was just taken:
+        //   -1-k           exact Newton step k (fresh factor at this x).  Quadratic convergence: with
+        //                  c ~ sl_k / sl_{k-1}^2 the error after this step is ~ sl_k^3 / sl_{k-1}^2.
+        //   0..999         stale-factor (previous EM iteration) chord sweep: only has to reach Newton's fast regime.
+        //   1000+k         chord sweep k with the factor computed earlier in THIS call (at a point ~1e-2 from the
+        //                  mode): contraction ~ |H(x_f)^-1 (H(x_f) - H(x*))| ~ 1e-2 per sweep, replaces re-factorising.
+        // states: 0 keep going with the same kind of step, 1 converged, 2 needs a fresh factorisation.
         int state;
         const double scale = 1.0 + xmax;
+        const double prev = steplen[trial];
         if (chord_it < 0) {
             state = (sl <= tol * scale) ? 1 : 0;
-            const double prev = steplen[trial];
             if (state == 0 && chord_it <= -2 && alpha == 1.0 && prev > 0.0 && sl < 0.1 * prev &&
                 sl * sl * sl / (prev * prev) <= 0.1 * tol * scale)
                 state = 1;
-        } else {
+        } else if (chord_it < 1000) {
             const double chord_goal = 1e-2;
-            const double prev = steplen[trial];
             state = (sl <= chord_goal * scale) ? 2 : 0;
             if (state == 0 && chord_it >= 1 && sl > 0.7 * prev) state = 2;
             // already converged (late EM: parameters barely move): certified by the observed contraction
             if (chord_it >= 1 && sl < 0.5 * prev && sl * (sl / prev) / (1.0 - sl / prev) <= tol * scale) state = 1;
             if (chord_it == 0 && sl <= 0.01 * tol * scale) state = 1;
+        } else {
+            const double rho = (prev > 0.0) ? sl / prev : 1.0;
+            state = 0;
+            if (rho < 0.5 && sl * rho / (1.0 - rho) <= 0.1 * tol * scale) state = 1;   // remaining error certified
+            else if (sl <= 0.01 * tol * scale) state = 1;                               // at the rounding floor
+            else if (rho > 0.3 || alpha < 1.0) state = 2;                               // contracts too slowly
         }
         steplen[trial] = sl;
         conv[trial] = state;
@@ -252,6 +259,11 @@ __global__ void __launch_bounds__(256) polish_kernel(double *__restrict__ x, con
     if (dmax <= max_rel * (1.0 + xmax))
         for (int i = threadIdx.x; i < n; i += blockDim.x) x[(size_t)trial * n + i] += dx[(size_t)trial * n + i];
     if (threadIdx.x == 0) steplen[trial] = dmax;
+}
+
+__global__ void scatter_slots_kernel(const int *act, int n, int *map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) map[act[i]] = i;
 }
 
 __global__ void iota_kernel(int *p, int n, int start) {
@@ -374,7 +386,7 @@ std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all) {
 namespace {
 struct LapWs {
     double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen;
-    int *conv, *actA, *actB, *cnt;
+    int *conv, *actA, *actB, *actC, *lslot, *cnt;
     int2 *pairs;
     double *L, *Dinv, *ZT;
     int chunk;
@@ -387,7 +399,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += 4 * align_up((size_t)R * n * 8);
     b += align_up((size_t)R * q * q * T * 8);
     b += 2 * align_up((size_t)R * 8);
-    b += 3 * align_up((size_t)R * 4) + 256;
+    b += 5 * align_up((size_t)R * 4) + 256;
     b += align_up((size_t)npairs_max * sizeof(int2));
     return b;
 }
@@ -429,6 +441,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
     w.W = (double *)take((size_t)R * q * q * T * 8);
     w.fcur = (double *)take((size_t)R * 8); w.steplen = (double *)take((size_t)R * 8);
     w.conv = (int *)take((size_t)R * 4); w.actA = (int *)take((size_t)R * 4); w.actB = (int *)take((size_t)R * 4);
+    w.actC = (int *)take((size_t)R * 4); w.lslot = (int *)take((size_t)R * 4);
     w.cnt = (int *)take(256);
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
     w.L = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
@@ -444,7 +457,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
 
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
-    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, chord_its = 0, chord_fallback = 0;
+    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, chord_its = 0, chord_fallback = 0, fresh_sweeps = 0;
     const double solve_bytes = 2.0 * (double)(ltl + nb) * PGPFA_TILE * 8;
     auto read_count = [&](int &dst) -> int {
         PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -493,7 +506,8 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             PGPFA_TRY(read_count(n_act));
             chord_fallback += n_act;
         }
-        // ---- phase B: exact Newton with fresh factorisations
+        // ---- phase B: exact Newton with fresh factorisations; every factor is re-used for a few chord sweeps
+        // (4 ms each for 1024 trials) before anything is factorised again
         for (int it = 0; it < max_newton && n_act > 0; it++) {
             pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
@@ -503,6 +517,8 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st, h));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_FACTOR] += (double)n_act * n * (double)n * n / 3.0;
+            scatter_slots_kernel<<<(n_act + 255) / 256, 256, 0, st>>>(act, n_act, w.lslot);
+            PGPFA_LAUNCH_CHECK();
             pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
             PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, act, n, n_act, st));
             pgpfa_prof_end(h, st);
@@ -512,12 +528,41 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
                                          niter, w.steplen, -1 - it, st));
             pgpfa_prof_end(h, st);
-            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, act_next, w.cnt);
-            PGPFA_LAUNCH_CHECK();
             total_factor_trials += n_act;
-            PGPFA_TRY(read_count(n_act));
-            int *tmp = act; act = act_next; act_next = tmp;
             if (it + 1 > max_it_used) max_it_used = it + 1;
+            // sweeps with the factor just computed; `act` keeps the list it was computed for
+            int *swp = act_next, *swp_next = w.actC;
+            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, swp, w.cnt);
+            PGPFA_LAUNCH_CHECK();
+            int n_swp = 0;
+            PGPFA_TRY(read_count(n_swp));
+            for (int cs = 0; cs < 8 && n_swp > 0; cs++) {
+                pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
+                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, swp, n_swp, q, T, st));
+                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, swp, n_swp, q, N, T, w.fcur, w.g, w.W, st));
+                pgpfa_prof_end(h, st);
+                pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
+                PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, swp, n, n_swp, st, -1, w.lslot));
+                pgpfa_prof_end(h, st);
+                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_swp * solve_bytes;
+                pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
+                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, swp, n_swp, q, T, st));
+                PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, swp, n_swp, q, N, T, tol, w.fcur, w.conv,
+                                             niter, w.steplen, 1000 + cs, st));
+                pgpfa_prof_end(h, st);
+                compact_active_kernel<<<1, 1024, 0, st>>>(swp, n_swp, w.conv, 1, swp_next, w.cnt);
+                PGPFA_LAUNCH_CHECK();
+                PGPFA_TRY(read_count(n_swp));
+                int *t2 = swp; swp = swp_next; swp_next = t2;
+                fresh_sweeps++;
+            }
+            // whoever is not converged (state 0: sweeps exhausted, state 2: contraction too slow) is re-factorised
+            int *outp = (act == w.actA) ? w.actB : w.actA;       // the sweep lists are dead by now
+            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 5, outp, w.cnt);
+            PGPFA_LAUNCH_CHECK();
+            PGPFA_TRY(read_count(n_act));
+            act = outp;
+            act_next = (act == w.actA) ? w.actB : w.actA;
         }
         not_converged += n_act;
         // ---- posterior at the mode: objective, factor, one more (free) Newton correction, inverse slices
@@ -561,7 +606,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         stats_out[4] = chord_its;
         stats_out[5] = chord_fallback;
         stats_out[6] = (chunk >= R) ? 1 : 0;     // the workspace now holds every trial's factor at its mode
-        stats_out[7] = 0;
+        stats_out[7] = fresh_sweeps;
     }
     return not_converged ? PGPFA_ERR_NOT_CONVERGED : PGPFA_OK;
 }

@@ -24,7 +24,7 @@ int pgpfa_i_timediag(const double *ZT, const int *act, double *vsm, int n, int q
 int pgpfa_i_logdet(const double *L, int n, int nslots, double *out, cudaStream_t st);
 int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, double *out, cudaStream_t st);
 int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
-                  int n, int nslots, cudaStream_t st, int lslot_base = -1);
+                  int n, int nslots, cudaStream_t st, int lslot_base = -1, const int *lslot_map = nullptr);
 
 #include <vector>
 #include "../../include/pgpfa_b200.h"

@@ -12,7 +12,8 @@ namespace {
 
 __global__ void __launch_bounds__(256) chol_solve_kernel(const double *__restrict__ L, const double *__restrict__ Dinv,
                                                          const double *__restrict__ rhs, double *__restrict__ out,
-                                                         double scale, const int *act, int nb, int n, int lslot_base) {
+                                                         double scale, const int *act, int nb, int n, int lslot_base,
+                                                         const int *__restrict__ lslot_map) {
     extern __shared__ double sm[];
     double *z = sm;                 // nb*64
     double *tmp = sm + nb * PGPFA_NB;  // 64
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double *__restric
     const long long ltl = (long long)nb * (nb + 1) / 2;
     // factor slot: position in the active list (fresh factorisation) or trial - base (factor kept from an
     // earlier call, stored by local trial index)
-    const int lslot = lslot_base >= 0 ? trial - lslot_base : slot;
+    // ... or lslot_map[trial] (factor computed for an earlier, longer active list)
+    const int lslot = lslot_map ? lslot_map[trial] : (lslot_base >= 0 ? trial - lslot_base : slot);
     const double *Ls = L + (size_t)lslot * ltl * PGPFA_TILE;
     const double *Ds = Dinv + (size_t)lslot * nb * PGPFA_TILE;
     for (int i = tid; i < nb * PGPFA_NB; i += 256) z[i] = (i < n) ? rhs[(size_t)trial * n + i] : 0.0;
@@ -115,14 +117,14 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double *__restric
 }  // namespace
 
 int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
-                  int n, int nslots, cudaStream_t st, int lslot_base) {
+                  int n, int nslots, cudaStream_t st, int lslot_base, const int *lslot_map) {
     if (nslots <= 0) return PGPFA_OK;
     const int nb = pgpfa_nb(n);
     const size_t smem = (size_t)(nb * PGPFA_NB + PGPFA_NB) * sizeof(double);
     if (smem > 48 * 1024) {
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    chol_solve_kernel<<<nslots, 256, smem, st>>>(L, Dinv, rhs, out, scale, act, nb, n, lslot_base);
+    chol_solve_kernel<<<nslots, 256, smem, st>>>(L, Dinv, rhs, out, scale, act, nb, n, lslot_base, lslot_map);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }

@@ -177,7 +177,7 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
                   allow=(_lib.ERR_NOT_CONVERGED,))
     res.stats = {"factorizations": stats[0], "max_newton_iters": stats[1], "not_converged": stats[2],
                  "chunk": stats[3], "chord_iters": stats[4], "chord_fallback_trials": stats[5],
-                 "factors_kept": bool(stats[6])}
+                 "factors_kept": bool(stats[6]), "fresh_chord_sweeps": stats[7]}
     return res
 
 
