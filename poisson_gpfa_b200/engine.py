@@ -181,6 +181,7 @@ class PPGPFAfit():
         self.optimParams = params
         self.infRes = infRes              # of the last batch processed in online EM (this rank's shard)
         self.processParamResults()
+        self.performSpikeCountAnalysis()
         self.learningTime = np.asarray(learningTime)
         self.inferenceTime = np.asarray(inferenceTime)
         self.CdOptimMethod = CdOptimMethod
@@ -209,6 +210,37 @@ class PPGPFAfit():
         else:
             (self.infRes_trueParams, self.nll_trueParams_all_traj, self.vlb_trueParams_all_traj, _) = \
                 inference.dualVariational(self.experiment, tp, optimizeLogLambda=self.optimLogLamb, reducer=self._reducer)
+
+    def performSpikeCountAnalysis(self):
+        """funs/engine.py:483-512 (post-fit diagnostics on the host: model-implied vs observed count moments)."""
+        ex = self.experiment
+        raster = np.concatenate([np.asarray(t['Y'], dtype=np.float64) for t in ex.data], axis=1)
+        ex.all_raster = raster
+        E_y_init, E_yy_init = util.getMeanCovYfromParams(self.initParams, ex)
+        E_y_opt, E_yy_opt = util.getMeanCovYfromParams(self.optimParams, ex)
+        E_y_obs, E_yy_obs = np.mean(raster, 1), np.cov(raster)
+        nrm = np.linalg.norm
+        with np.errstate(all='ignore'):
+            if hasattr(ex, 'params'):
+                E_y_true, E_yy_true = util.getMeanCovYfromParams(ex.params, ex)
+                self.E_y_true_params, self.E_yy_true_params = E_y_true, E_yy_true
+                v = np.var(E_y_true)
+                self.mean_err_optim_true = np.dot(E_y_true - E_y_opt, E_y_true - E_y_opt) / v / self.numTrials
+                self.mean_err_init_true = np.dot(E_y_true - E_y_init, E_y_true - E_y_init) / v / self.numTrials
+                self.cov_err_optim_true = nrm(E_yy_true - E_yy_opt) / nrm(E_yy_obs)
+                self.cov_err_init_true = nrm(E_yy_true - E_yy_init) / nrm(E_yy_obs)
+                self.JSdiv_cov_optim_true = util.JSLogdetDiv(E_yy_opt, E_yy_true)
+                self.JSdiv_cov_init_true = util.JSLogdetDiv(E_yy_init, E_yy_true)
+            self.E_y_init_params, self.E_y_optim_params = E_y_init, E_y_opt
+            self.E_yy_init_params, self.E_yy_optim_params = E_yy_init, E_yy_opt
+            self.E_y_obs, self.E_yy_obs = E_y_obs, E_yy_obs
+            v = np.var(E_y_obs)
+            self.mean_err_optim_obs = np.dot(E_y_obs - E_y_opt, E_y_obs - E_y_opt) / v / self.numTrials
+            self.mean_err_init_obs = np.dot(E_y_obs - E_y_init, E_y_obs - E_y_init) / v / self.numTrials
+            self.cov_err_optim_obs = nrm(E_yy_obs - E_yy_opt) / nrm(E_yy_obs)
+            self.cov_err_init_obs = nrm(E_yy_obs - E_yy_init) / nrm(E_yy_obs)
+            self.JSdiv_cov_optim_obs = util.JSLogdetDiv(E_yy_opt, E_yy_obs)
+            self.JSdiv_cov_init_obs = util.JSLogdetDiv(E_yy_init, E_yy_obs)
 
     def processParamResults(self):
         """funs/engine.py:545-597 (host-side bookkeeping over paramSeq; diagnostics, not hot path)."""

@@ -90,6 +90,21 @@ def initializeParams(xdim, ydim, experiment=None):
     return {'C': evecs, 'd': gamma, 'tau': np.random.rand(xdim) * 0.5 + 0.1}
 
 
+def JSLogdetDiv(X, Y):
+    """funs/util.py:21-22 (post-fit diagnostic, host side)."""
+    return np.log(np.linalg.det((X + Y) / 2)) - 1 / 2 * np.log(np.linalg.det(X.dot(Y)))
+
+
+def getMeanCovYfromParams(params, experiment):
+    """funs/util.py:24-39: model-implied mean / second moment of the spike counts (post-fit diagnostic, host side)."""
+    rho = np.ravel(params['d'])
+    lamb = np.dot(params['C'], np.asarray(params['C']).T)
+    E_y = np.exp(1 / 2 * np.diag(lamb) + rho)
+    E_yy = np.outer(E_y, E_y) * np.exp(lamb / 2)
+    E_yy[np.diag_indices_from(E_yy)] = E_y + np.exp(np.diag(lamb) / 2) * E_y ** 2
+    return E_y, E_yy
+
+
 class Experiment:
     """Minimal duck-typed experiment (attributes read by the hot path: funs/engine.py:131-136)."""
 
