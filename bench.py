@@ -223,7 +223,7 @@ def run_ours(args):
         barrier()
         if i > 0:
             e2e_t.append(time.perf_counter() - t0)
-        h2d = Y_pin.numel() * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
+        h2d = (hi - lo) * N * T * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
         d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8
     e2e_sec = float(np.mean(e2e_t)) if e2e_t else float("nan")
     if world > 1:

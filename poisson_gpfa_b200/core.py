@@ -172,87 +172,119 @@ class DeviceTrials:
         P = kn.pautosum(est.vsmGP, est.x)
         return self.reducer.sum_tensor(P)
 
-    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, gtol=1e-9, max_eval=80):
-        """q independent scalar minimisations over p = log(1/tau_bins^2) (funs/learning.py:257-293,
-        :771-830), all latents in lock-step: bracket the first zero of the gradient in the descent
-        direction from the old tau, then Illinois (safeguarded secant) refinement.  One device
-        evaluation per iteration serves all latents.  Returns (tau_seconds (q), details)."""
+    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, xtol=2e-11, max_rounds=14, ncand=5):
+        """q independent scalar minimisations over p = log(1/tau_bins^2) (funs/learning.py:257-293, :771-830).
+        The reference hands each to scipy (BFGS / TNC) from p0 = the old tau; the result is the first zero of
+        the gradient in the descent direction from p0.  Here all latents advance in lock-step and every device
+        launch evaluates `ncand` candidate points per latent (the T x T factorisations are latency-bound, so
+        candidates are free): round 1 brackets the sign change of the gradient around p0, later rounds place
+        the candidates around the inverse-cubic interpolant of the bracket's neighbours (error ~ width^4), so
+        3-4 launches reach |dp| < 2e-11.  Returns (tau_seconds (q), details)."""
         q, T = params.q, self.T
         R = float(self.R_total if numTrials is None else numTrials)
-        if self._tau_ws is None or self._tau_ws[0] != (q, T):
-            self._tau_ws = ((q, T), _lib.workspace(_lib.lib.pgpfa_tau_eval_workspace_bytes(q, T)))
+        m = int(ncand)
+        key = (q, T, m)
+        if self._tau_ws is None or self._tau_ws[0] != key:
+            self._tau_ws = (key, _lib.workspace(_lib.lib.pgpfa_tau_eval_workspace_bytes(q * m, T)))
         tau_old = params.tau
+        P_rep = Psum.repeat(m, 1, 1).contiguous()               # slot = c*q + k  (data movement only)
+        tau_old_rep = tau_old.repeat(m).contiguous()
         pw = 0.0 if prior_step is None else 1.0 / float(prior_step) ** 2
         nev = [0]
 
-        def fg(p_np):
+        def fg(cands):                                          # (m,q) -> f, g (m,q)
             nev[0] += 1
-            c, g = kn.tau_eval(_lib.dev_f64(p_np), Psum, R, T, EPS_NOISE, pw, tau_old, self.binSize,
-                               ws=self._tau_ws[1])
-            return c.cpu().numpy(), g.cpu().numpy()
+            c, g = kn.tau_eval(_lib.dev_f64(np.ascontiguousarray(cands).reshape(-1)), P_rep, R, T, EPS_NOISE, pw,
+                               tau_old_rep, self.binSize, ws=self._tau_ws[1])
+            both = torch.stack([c, g]).cpu().numpy()
+            return both[0].reshape(m, q), both[1].reshape(m, q)
 
         oldTau_bins = tau_old.cpu().numpy() * 1000.0 / self.binSize
         p0 = np.log(1.0 / oldTau_bins ** 2)
-        p, (f, g) = p0.copy(), fg(p0)
-        f0 = f.copy()
-        # bracket: walk downhill with doubling steps until the gradient changes sign
-        a, ga = p.copy(), g.copy()
-        b, gb = p.copy(), g.copy()
-        stepsz = np.full(q, 0.25)
-        have = np.abs(g) <= 0.0
-        for _ in range(30):
-            if have.all():
-                break
-            trial = np.where(have, b, b - np.sign(ga) * stepsz)
-            trial = np.clip(trial, -40.0, 20.0)
-            ft, gt = fg(trial)
-            flip = (np.sign(gt) != np.sign(ga)) | (gt == 0.0)
-            upd = ~have
-            # keep `a` as the last point with the original sign, `b` the first point with the other sign
-            mv = upd & ~flip
-            a[mv], ga[mv] = trial[mv], gt[mv]
-            b[upd], gb[upd] = trial[upd], gt[upd]
-            have = have | flip
-            stepsz = np.where(have, stepsz, stepsz * 2.0)
-            if nev[0] >= max_eval:
-                break
-        # Illinois (safeguarded secant) iterations on g over [a,b], sign(ga) != sign(gb); a latent stops
-        # when the proposed move is below xtol (superlinear convergence: the move estimates the error)
-        side = np.zeros(q, dtype=int)
-        pick_a = np.abs(ga) < np.abs(gb)
-        x, gx, fx = np.where(pick_a, a, b), np.where(pick_a, ga, gb), f.copy()
-        conv = ~have | (gx == 0.0)
-        xtol = 1e-11
-        while not conv.all() and nev[0] < max_eval:
-            denom = gb - ga
-            with np.errstate(divide='ignore', invalid='ignore'):
-                c = np.where(denom != 0.0, b - gb * (b - a) / denom, 0.5 * (a + b))
-            lo, hi = np.minimum(a, b), np.maximum(a, b)
-            c = np.where((c > lo) & (c < hi), c, 0.5 * (a + b))
-            small = (np.abs(c - x) <= xtol * (1.0 + np.abs(x))) | (np.abs(b - a) <= xtol * (1.0 + np.abs(a)))
-            x = np.where(~conv & small, c, x)
-            conv = conv | small
-            if conv.all():
-                break
-            c = np.where(conv, x, c)
-            fc, gc = fg(c)
+        offs = np.array([0.0, -0.2, 0.2, -0.5, 0.5])[:m] if m >= 3 else np.array([0.0, -0.2, 0.2])[:m]
+        cands = p0[None, :] + offs[:, None]
+        f, g = fg(cands)
+        pts = [sorted(zip(cands[:, k], g[:, k], f[:, k])) for k in range(q)]       # per latent: (p, g, f) ascending in p
+        g0, f0 = g[0].copy(), f[0].copy()
+        done = np.zeros(q, dtype=bool)
+        p_star = p0.copy()
+        bracketed = np.zeros(q, dtype=bool)
+
+        def bracket_of(k):
+            """Index i with a sign change of g between pts[k][i] and pts[k][i+1], nearest to p0 on the descent side."""
+            P = pts[k]
+            idx0 = min(range(len(P)), key=lambda i: abs(P[i][0] - p0[k]))
+            if P[idx0][1] == 0.0:
+                return ('exact', idx0)
+            rng = range(idx0, len(P) - 1) if P[idx0][1] < 0 else range(idx0 - 1, -1, -1)
+            for i in rng:
+                if P[i][1] == 0.0:
+                    return ('exact', i)
+                if P[i][1] < 0.0 <= P[i + 1][1]:
+                    return ('br', i)
+            return ('none', len(P) - 1 if P[idx0][1] < 0 else 0)
+
+        def interpolate(k, i):
+            """Zero of g inside (P[i], P[i+1]) by inverse polynomial interpolation through up to 4 neighbours."""
+            P = pts[k]
+            a, ga = P[i][0], P[i][1]
+            b, gb = P[i + 1][0], P[i + 1][1]
+            sel = P[max(0, i - 1):i + 3]
+            gs = np.array([t[1] for t in sel]); ps = np.array([t[0] for t in sel])
+            c = a - ga * (b - a) / (gb - ga)
+            if len(sel) >= 3 and np.all(np.diff(gs) > 0):
+                est = 0.0
+                for u in range(len(sel)):                       # Lagrange form of p(g) at g = 0
+                    wgt = 1.0
+                    for v in range(len(sel)):
+                        if v != u:
+                            wgt *= (0.0 - gs[v]) / (gs[u] - gs[v])
+                    est += wgt * ps[u]
+                if a < est < b:
+                    c = est
+            return c, a, b
+
+        for rnd in range(max_rounds):
+            cands = np.tile(p_star[None, :], (m, 1))
             for k in range(q):
-                if conv[k]:
+                if done[k]:
                     continue
-                if gc[k] == 0.0:
-                    conv[k] = True
-                elif np.sign(gc[k]) == np.sign(gb[k]):
-                    b[k], gb[k] = c[k], gc[k]
-                    if side[k] == -1:
-                        ga[k] *= 0.5
-                    side[k] = -1
-                else:
-                    a[k], ga[k] = c[k], gc[k]
-                    if side[k] == 1:
-                        gb[k] *= 0.5
-                    side[k] = 1
-                x[k], gx[k], fx[k] = c[k], gc[k], fc[k]
-        p_new = np.where(have, x, p0)
+                kind, i = bracket_of(k)
+                P = pts[k]
+                if kind == 'exact':
+                    p_star[k], done[k], bracketed[k] = P[i][0], True, True
+                    continue
+                if kind == 'none':                               # walk further downhill with growing steps
+                    edge = P[i][0]
+                    span = max(0.5, abs(edge - p0[k]))
+                    sgn = 1.0 if P[i][1] < 0 else -1.0
+                    cands[:, k] = np.clip(edge + sgn * span * np.array([0.5, 1.0, 2.0, 4.0, 8.0])[:m], -40.0, 20.0)
+                    if abs(edge) >= 20.0:
+                        done[k] = True                           # monotone cost: keep the old tau (flagged)
+                    continue
+                bracketed[k] = True
+                c, a, b = interpolate(k, i)
+                w = b - a
+                p_star[k] = c
+                if w <= xtol * (1.0 + abs(a)):
+                    done[k] = True
+                    continue
+                h1 = min(max(8.0 * w ** 4, 4.0 * xtol * (1.0 + abs(c))), w / 16.0)
+                h2 = min(max(0.5 * w ** 2, 4.0 * h1), w / 4.0)
+                pr = np.array([c, c - h1, c + h1, c - h2, c + h2])[:m]
+                lo, hi = a + 1e-3 * w, b - 1e-3 * w
+                cands[:, k] = np.clip(pr, lo, hi)
+            if done.all():
+                break
+            f, g = fg(cands)
+            for k in range(q):
+                if not done[k]:
+                    have = {t[0] for t in pts[k]}
+                    pts[k] = sorted(pts[k] + [(cands[c_, k], g[c_, k], f[c_, k]) for c_ in range(m) if cands[c_, k] not in have])
+        p_new = np.where(bracketed, p_star, p0)
         tau_bins = (1.0 / np.exp(p_new)) ** 0.5
-        details = {'p': p_new, 'p0': p0, 'grad': gx, 'fun': fx, 'fun0': f0, 'nfev': nev[0], 'bracketed': have}
+        fun = np.array([min(pts[k], key=lambda t: abs(t[0] - p_new[k]))[2] for k in range(q)])
+        gr = np.array([min(pts[k], key=lambda t: abs(t[0] - p_new[k]))[1] for k in range(q)])
+        details = {'p': p_new, 'p0': p0, 'grad': gr, 'fun': fun, 'fun0': f0, 'grad0': g0, 'nfev': nev[0],
+                   'bracketed': bracketed}
         return tau_bins * self.binSize / 1000.0, details

@@ -20,48 +20,50 @@ _f64 = _lib.dev_f64
 # ----------------------------------------------------------------------------------------------
 # helpers: experiments <-> device
 # ----------------------------------------------------------------------------------------------
+def _host_rows(experiment, lo, hi):
+    """Rows [lo, hi) of the spike counts as a host array / pinned tensor (no copy of the other trials)."""
+    Y_all = getattr(experiment, 'Y_all', None)
+    if Y_all is not None:          # optional fast path: all counts as one (R,N,T) array or pinned tensor
+        return torch.as_tensor(Y_all)[lo:hi]
+    return torch.from_numpy(np.stack([np.asarray(experiment.data[r]['Y'], dtype=np.float64) for r in range(lo, hi)]))
+
+
 def _full_counts(experiment):
-    """All trials of an experiment as one (R,N,T) float64 device tensor, uploaded once and cached on
-    the experiment object; mini-batches made by util.subsampleTrials are gathered on the device from
-    the resident parent."""
+    """All trials of an experiment as one (R,N,T) float64 device tensor, uploaded once and cached on the experiment
+    object.  Only needed for parents of mini-batches (util.subsampleTrials), which are gathered on the device."""
     y = experiment.__dict__.get('_pgpfa_y')
-    if y is not None and y.shape[0] == len(experiment.data):
-        return y
-    parent = experiment.__dict__.get('_pgpfa_parent')
-    if parent is not None and hasattr(experiment, 'batchTrIdx'):
-        idx = torch.as_tensor(np.asarray(experiment.batchTrIdx), device="cuda", dtype=torch.long)
-        y = _full_counts(parent).index_select(0, idx).contiguous()
-    elif getattr(experiment, 'Y_all', None) is not None:
-        # optional fast path: all counts as one (R,N,T) array / pinned tensor instead of per-trial arrays
-        y = torch.as_tensor(experiment.Y_all).to(device="cuda", dtype=torch.float64, non_blocking=True).contiguous()
-    else:
-        y = _f64(np.stack([np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data]))
-    experiment.__dict__['_pgpfa_y'] = y
+    if y is None or y.shape[0] != len(experiment.data):
+        y = _host_rows(experiment, 0, len(experiment.data)).to(device="cuda", dtype=torch.float64).contiguous()
+        experiment.__dict__['_pgpfa_y'] = y
     return y
 
 
 def upload_counts(experiment):
-    """Re-copy the host spike counts into the resident device buffer (keeps workspaces and kept factors)."""
-    y = experiment.__dict__.get('_pgpfa_y')
-    if y is None:
-        return _full_counts(experiment)
-    if getattr(experiment, 'Y_all', None) is not None:
-        y.copy_(torch.as_tensor(experiment.Y_all), non_blocking=True)
-    else:
-        y.copy_(torch.from_numpy(np.stack([np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data])))
-    return y
+    """Re-copy this rank's host spike counts into the resident device buffer (keeps workspaces and kept factors)."""
+    dt = experiment.__dict__.get('_pgpfa_dev')
+    if dt is None:
+        return device_trials(experiment).y
+    dt.y.copy_(_host_rows(experiment, dt.offset, dt.offset + dt.R), non_blocking=True)
+    return dt.y
 
 
 def device_trials(experiment, reducer=None):
-    """This rank's shard of the experiment (contiguous block of trials).  Every rank keeps
-    the full count tensor resident (164 MB at the 1024-trial shape) and works on its own block."""
+    """This rank's shard of the experiment (contiguous block of trials).  Batch mode uploads only the
+    shard; a mini-batch made by util.subsampleTrials is gathered on the device from its (fully resident) parent and
+    then split across the ranks."""
     reducer = reducer if reducer is not None else Reducer()
+    R = len(experiment.data)
     cached = experiment.__dict__.get('_pgpfa_dev')
-    if cached is not None and cached.R_total == len(experiment.data) and cached.reducer.world_size == reducer.world_size:
+    if cached is not None and cached.R_total == R and cached.reducer.world_size == reducer.world_size:
         return cached
-    y = _full_counts(experiment)
-    lo, hi = shard_bounds(y.shape[0], reducer.world_size, reducer.rank)
-    dt = DeviceTrials(y[lo:hi], experiment.binSize, reducer, R_total=y.shape[0], offset=lo)
+    lo, hi = shard_bounds(R, reducer.world_size, reducer.rank)
+    parent = experiment.__dict__.get('_pgpfa_parent')
+    if parent is not None and hasattr(experiment, 'batchTrIdx'):
+        idx = torch.as_tensor(np.asarray(experiment.batchTrIdx)[lo:hi], device="cuda", dtype=torch.long)
+        y = _full_counts(parent).index_select(0, idx).contiguous()
+    else:
+        y = _host_rows(experiment, lo, hi).to(device="cuda", dtype=torch.float64).contiguous()
+    dt = DeviceTrials(y, experiment.binSize, reducer, R_total=R, offset=lo)
     experiment.__dict__['_pgpfa_dev'] = dt
     return dt
 
