@@ -213,10 +213,9 @@ def run_ours(args):
         t0 = time.perf_counter()
         inference.upload_counts(exp)                       # H2D of this step's inputs (pinned -> HBM)
         prev = None
-        if modes_host is not None:
-            full = np.zeros((R, n))
-            full[lo:hi] = modes_host.reshape(hi - lo, n)
-            prev = list(full)
+        if modes_host is not None:                         # per-trial modes of the previous iteration, host side
+            prev = np.zeros((R, n))
+            prev[lo:hi] = modes_host.reshape(hi - lo, n)
         infRes, lik_e, optim = inference.laplace(exp, host_params, prevOptimRes=prev, reducer=red)
         host_params, det = learning.updateParams(host_params, infRes, exp)
         modes_host = optim.tensor.cpu().numpy()            # D2H of the step's results

@@ -172,7 +172,7 @@ class DeviceTrials:
         P = kn.pautosum(est.vsmGP, est.x)
         return self.reducer.sum_tensor(P)
 
-    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, xtol=2e-11, max_rounds=14, ncand=5):
+    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, xtol=1e-10, max_rounds=14, ncand=9):
         """q independent scalar minimisations over p = log(1/tau_bins^2) (funs/learning.py:257-293, :771-830).
         The reference hands each to scipy (BFGS / TNC) from p0 = the old tau; the result is the first zero of
         the gradient in the descent direction from p0.  Here all latents advance in lock-step and every device
@@ -201,7 +201,7 @@ class DeviceTrials:
 
         oldTau_bins = tau_old.cpu().numpy() * 1000.0 / self.binSize
         p0 = np.log(1.0 / oldTau_bins ** 2)
-        offs = np.array([0.0, -0.2, 0.2, -0.5, 0.5])[:m] if m >= 3 else np.array([0.0, -0.2, 0.2])[:m]
+        offs = np.array([0.0, -0.1, 0.1, -0.25, 0.25, -0.5, 0.5, -1.0, 1.0])[:m]
         cands = p0[None, :] + offs[:, None]
         f, g = fg(cands)
         pts = [sorted(zip(cands[:, k], g[:, k], f[:, k])) for k in range(q)]       # per latent: (p, g, f) ascending in p
@@ -232,6 +232,7 @@ class DeviceTrials:
             sel = P[max(0, i - 1):i + 3]
             gs = np.array([t[1] for t in sel]); ps = np.array([t[0] for t in sel])
             c = a - ga * (b - a) / (gb - ga)
+            err = 0.5 * (b - a) ** 2                              # secant: error ~ |g''/2g'| (c-a)(b-c)
             if len(sel) >= 3 and np.all(np.diff(gs) > 0):
                 est = 0.0
                 for u in range(len(sel)):                       # Lagrange form of p(g) at g = 0
@@ -242,7 +243,9 @@ class DeviceTrials:
                     est += wgt * ps[u]
                 if a < est < b:
                     c = est
-            return c, a, b
+                    span = ps.max() - ps.min()
+                    err = 0.25 * (b - a) ** 2 * span ** (len(sel) - 2)   # ~ product of the distances to the nodes
+            return c, a, b, err
 
         for rnd in range(max_rounds):
             cands = np.tile(p_star[None, :], (m, 1))
@@ -258,20 +261,21 @@ class DeviceTrials:
                     edge = P[i][0]
                     span = max(0.5, abs(edge - p0[k]))
                     sgn = 1.0 if P[i][1] < 0 else -1.0
-                    cands[:, k] = np.clip(edge + sgn * span * np.array([0.5, 1.0, 2.0, 4.0, 8.0])[:m], -40.0, 20.0)
+                    cands[:, k] = np.clip(edge + sgn * span * (0.5 * 1.7 ** np.arange(m)), -40.0, 20.0)
                     if abs(edge) >= 20.0:
                         done[k] = True                           # monotone cost: keep the old tau (flagged)
                     continue
                 bracketed[k] = True
-                c, a, b = interpolate(k, i)
+                c, a, b, err = interpolate(k, i)
                 w = b - a
                 p_star[k] = c
-                if w <= xtol * (1.0 + abs(a)):
+                if err <= xtol * (1.0 + abs(c)) or w <= xtol * (1.0 + abs(a)):
                     done[k] = True
                     continue
-                h1 = min(max(8.0 * w ** 4, 4.0 * xtol * (1.0 + abs(c))), w / 16.0)
-                h2 = min(max(0.5 * w ** 2, 4.0 * h1), w / 4.0)
-                pr = np.array([c, c - h1, c + h1, c - h2, c + h2])[:m]
+                h1 = min(max(2.0 * err, 4.0 * xtol * (1.0 + abs(c))), w / 16.0)
+                h2 = min(max(4.0 * h1, 0.25 * w ** 2), w / 4.0)
+                hs = [h1, h2] + [min(h2 * 4.0 ** e, w / 2.5) for e in range(1, (m - 1) // 2 - 1)]
+                pr = np.array([c] + [c + sg * hh for hh in hs for sg in (-1.0, 1.0)])[:m]
                 lo, hi = a + 1e-3 * w, b - 1e-3 * w
                 cands[:, k] = np.clip(pr, lo, hi)
             if done.all():

@@ -97,7 +97,47 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
 // ---------------------------------------------------------------------------------------------
 // Diagonal-tile kernel: SYRK update + 64x64 Cholesky + 64x64 triangular inverse (in shared memory)
 // ---------------------------------------------------------------------------------------------
+// row index of the bi-th block in a row-major enumeration of a lower-triangular block grid (bi = rb(rb+1)/2 + cb)
+__constant__ unsigned char c_tri_row[28] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6};
+
 #define SLD 65
+// One warp factors the 8x8 diagonal sub-block b of S in place (lower triangle) and writes its inverse to
+// DI[b]: lane i (mod 8) owns row i in registers, pivots travel by shuffle.
+__device__ __forceinline__ void diag8_factor(double *S, double *DI, int *bad_sm, int b, int jtile, int lane) {
+    const int i = lane & 7;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[c] = (c <= i) ? S[(8 * b + i) * SLD + 8 * b + c] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double piv = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(piv > 0.0)) { if (lane == 0 && *bad_sm == 0) *bad_sm = jtile * PGPFA_NB + 8 * b + k + 1; piv = 1.0; }
+        const double dd = sqrt(piv), dinv = 1.0 / dd;
+        a[k] = (i == k) ? dd : ((i > k) ? a[k] * dinv : a[k]);
+#pragma unroll
+        for (int c = k + 1; c < 8; c++) {
+            const double lck = __shfl_sync(0xffffffffu, a[k], c);
+            if (i >= c) a[c] -= a[k] * lck;
+        }
+    }
+    // inverse of the sub-block: lane i owns column i of it (forward substitution)
+    double xv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const double lrr = __shfl_sync(0xffffffffu, a[r], r);
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < r) { const double lrk = __shfl_sync(0xffffffffu, a[k], r); sacc += lrk * xv[k]; }
+        xv[r] = (r < i) ? 0.0 : ((r == i) ? 1.0 / lrr : -sacc / lrr);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) if (c <= i) S[(8 * b + i) * SLD + 8 * b + c] = a[c];
+#pragma unroll
+        for (int r = 0; r < 8; r++) DI[b * 64 + r * 8 + i] = xv[r];
+    }
+}
 // acc holds sum_k L(j,k) L(j,k)^T for the diagonal tile j of this slot: form S = A(j,j) - acc in shared
 // memory, factor it, invert the factor, and write L(j,j), Dinv_j and (optionally) ZT(j,j).
 // Must be entered by all threads with every earlier use of the shared staging area finished (__syncthreads).
@@ -125,45 +165,13 @@ __device__ __forceinline__ void diag_epilogue(const FactorArgs &a, unsigned char
     double *TT = DI + 8 * 64;                 // [7][8][8] scratch for the inverse
     int *bad_sm = reinterpret_cast<int *>(TT + 7 * 64);
     if (tid == 0) *bad_sm = 0;
+    // Software pipeline over the 8 sub-block columns: while warp 0 factors and inverts diagonal sub-block b+1
+    // (a serial chain of shuffles, square roots and divisions), warps 1-3 apply the rank-8 trailing update of
+    // step b to the rest of the tile.
+    __syncthreads();
+    if (warp == 0) diag8_factor(S, DI, bad_sm, 0, j, lane);
     for (int b = 0; b < 8; b++) {
-        __syncthreads();
-        if (warp == 0) {
-            // 8x8 diagonal sub-block: lane i (mod 8) owns row i in registers, pivots travel by shuffle
-            const int i = lane & 7;
-            double a[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) a[c] = (c <= i) ? S[(8 * b + i) * SLD + 8 * b + c] : 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                double piv = __shfl_sync(0xffffffffu, a[k], k);
-                if (!(piv > 0.0)) { if (lane == 0 && *bad_sm == 0) *bad_sm = j * PGPFA_NB + 8 * b + k + 1; piv = 1.0; }
-                const double dd = sqrt(piv), dinv = 1.0 / dd;
-                a[k] = (i == k) ? dd : ((i > k) ? a[k] * dinv : a[k]);
-#pragma unroll
-                for (int c = k + 1; c < 8; c++) {
-                    const double lck = __shfl_sync(0xffffffffu, a[k], c);
-                    if (i >= c) a[c] -= a[k] * lck;
-                }
-            }
-            // inverse of the sub-block: lane i owns column i of it (forward substitution)
-            double xv[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const double lrr = __shfl_sync(0xffffffffu, a[r], r);
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (k < r) { const double lrk = __shfl_sync(0xffffffffu, a[k], r); sacc += lrk * xv[k]; }
-                xv[r] = (r < i) ? 0.0 : ((r == i) ? 1.0 / lrr : -sacc / lrr);
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int c = 0; c < 8; c++) if (c <= i) S[(8 * b + i) * SLD + 8 * b + c] = a[c];
-#pragma unroll
-                for (int r = 0; r < 8; r++) DI[b * 64 + r * 8 + i] = xv[r];
-            }
-        }
-        __syncthreads();
+        __syncthreads();                               // DI_b and the factored sub-block b are visible
         // panel below the sub-block: P = S_panel * Dinv_b^T (one thread per row)
         {
             const int r = 8 * (b + 1) + tid;
@@ -183,21 +191,35 @@ __device__ __forceinline__ void diag_epilogue(const FactorArgs &a, unsigned char
             }
         }
         __syncthreads();
-        // trailing update of the remaining lower triangle: 8x8 blocks (rb >= cb > b), 64 threads per block
-        {
-            const int m = 7 - b;                       // remaining block rows
-            const int nblk = m * (m + 1) / 2;
-            const int half = tid >> 6, e = tid & 63, er = e >> 3, ec = e & 7;
-            for (int bi = half; bi < nblk; bi += 2) {
-                // bi -> (rb, cb) in the lower triangle of an m x m block grid
-                int rb = 0, acc_i = 0;
-                while (acc_i + rb + 1 <= bi) { acc_i += rb + 1; rb++; }
-                const int cb = bi - acc_i;
-                const int r = 8 * (b + 1 + rb) + er, c2 = 8 * (b + 1 + cb) + ec;
+        if (b == 7) break;
+        const int m = 7 - b;                           // remaining block rows / columns
+        if (warp == 0) {
+            // next diagonal sub-block first (64 elements, 2 per lane), then its factorisation
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                const int e = lane + 32 * h2, er = e >> 3, ec = e & 7;
+                const int r = 8 * (b + 1) + er, c2 = 8 * (b + 1) + ec;
                 double sum = 0.0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) sum += S[r * SLD + 8 * b + k] * S[c2 * SLD + 8 * b + k];
                 if (c2 <= r) S[r * SLD + c2] -= sum;
+            }
+            __syncwarp();
+            diag8_factor(S, DI, bad_sm, b + 1, j, lane);
+        } else {
+            // remaining 8x8 blocks (rb >= cb >= 1, not (1,1)) of the m x m trailing grid, 3 warps, 2 elements per lane
+            const int nblk = m * (m + 1) / 2;
+            for (int bi = 1 + (warp - 1); bi < nblk; bi += 3) {
+                const int rb = c_tri_row[bi], cb = bi - rb * (rb + 1) / 2;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int e = lane + 32 * h2, er = e >> 3, ec = e & 7;
+                    const int r = 8 * (b + 1 + rb) + er, c2 = 8 * (b + 1 + cb) + ec;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sum += S[r * SLD + 8 * b + k] * S[c2 * SLD + 8 * b + k];
+                    if (c2 <= r) S[r * SLD + c2] -= sum;
+                }
             }
         }
     }

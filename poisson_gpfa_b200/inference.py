@@ -201,9 +201,13 @@ def laplace(experiment, params, prevOptimRes=None, returnOptimRes=True, verbose=
     if prevOptimRes is not None:
         if isinstance(prevOptimRes, _TrialView) and prevOptimRes.tensor.shape[0] == trials.R:
             x0 = prevOptimRes.tensor.reshape(trials.R, p.q, T)
-        else:     # a reference-style list over ALL trials: keep this rank's block
-            sel = range(trials.offset, trials.offset + trials.R) if len(prevOptimRes) == trials.R_total else range(trials.R)
-            x0 = _f64(np.stack([np.asarray(prevOptimRes[i], dtype=np.float64).reshape(p.q, T) for i in sel]))
+        else:     # a reference-style list (or 2-D array) over ALL trials: keep this rank's block
+            lo_ = trials.offset if len(prevOptimRes) == trials.R_total else 0
+            if isinstance(prevOptimRes, np.ndarray) and prevOptimRes.ndim == 2:
+                x0 = _f64(prevOptimRes[lo_:lo_ + trials.R].reshape(trials.R, p.q, T))
+            else:
+                x0 = _f64(np.stack([np.asarray(prevOptimRes[i], dtype=np.float64).reshape(p.q, T)
+                                    for i in range(lo_, lo_ + trials.R)]))
     est = trials.estep_laplace(p, x0=x0, tol=tol)
     if verbose:
         print('laplace inference: %d trials, Newton iterations max %d, factorisations %d'
