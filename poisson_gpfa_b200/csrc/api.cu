@@ -97,13 +97,6 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
         delete h;
         return PGPFA_ERR_CUDA;
     }
-    int lo_prio = 0, hi_prio = 0;
-    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-    PGPFA_CUDA_TRY(cudaStreamCreateWithPriority(&h->s_crit, cudaStreamNonBlocking, hi_prio));
-    PGPFA_CUDA_TRY(cudaStreamCreateWithPriority(&h->s_bulk, cudaStreamNonBlocking, lo_prio));
-    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join_a, cudaEventDisableTiming));
-    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming));
     *out = h;
     return PGPFA_OK;
 }
@@ -111,10 +104,6 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
 extern "C" int pgpfa_destroy(pgpfa_handle_t h) {
     if (!h) return PGPFA_OK;
     if (h->pinned) cudaFreeHost(h->pinned);
-    for (auto e : h->ev_diag) cudaEventDestroy(e);
-    for (auto e : h->ev_rest) cudaEventDestroy(e);
-    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join_a); cudaEventDestroy(h->ev_join_b);
-    cudaStreamDestroy(h->s_crit); cudaStreamDestroy(h->s_bulk);
     delete h;
     return PGPFA_OK;
 }

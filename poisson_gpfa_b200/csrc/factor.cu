@@ -77,12 +77,12 @@ struct FactorArgs {
     double *L;          // slots x ltiles x 4096
     double *Dinv;       // slots x nb x 4096
     double *ZT;         // slots x ltiles x 4096 (packed upper) or nullptr
+    float *L32, *D32;   // optional FP32 mirrors of L / Dinv (inexact chord sweeps stream half the bytes)
     const int *act;     // slot -> trial, or nullptr (trial = slot)
     int *info;          // per trial: 0 ok, >0 first non-positive pivot (1-based)
     int nb;
     int step;
     int mode;           // panel kernel: 0 = Cholesky panel, 1 = triangular-inverse row
-    int tile0;          // panel kernel, mode 0: first tile row handled is step + 1 + tile0
     int nslots, ntiles; // panel kernel, mode 0: 1-D grid decode (ntiles tile rows per slot)
     int fuse;           // panel kernel, mode 0: first-tile CTAs also factor diagonal tile step+1
 };
@@ -251,11 +251,16 @@ __device__ __forceinline__ void diag_epilogue(const FactorArgs &a, unsigned char
     double *Lt = Ls + ltile(j, j) * PGPFA_TILE;
     double *Dt = a.Dinv + ((size_t)slot * a.nb + j) * PGPFA_TILE;
     double *Zt = a.ZT ? a.ZT + ((size_t)slot * ltl + utile(j, j, a.nb)) * PGPFA_TILE : nullptr;
+    float *Lt32 = a.L32 ? a.L32 + ((size_t)slot * ltl + ltile(j, j)) * PGPFA_TILE : nullptr;
+    float *Dt32 = a.D32 ? a.D32 + ((size_t)slot * a.nb + j) * PGPFA_TILE : nullptr;
     for (int off = tid; off < PGPFA_TILE; off += PGPFA_GEMM_THREADS) {
         const int r = (((off >> 6) & 7) << 3) + ((off >> 3) & 7);
         const int c = ((off >> 11) << 5) + (((off >> 9) & 3) << 3) + (off & 7);
-        Lt[off] = (c <= r) ? S[r * SLD + c] : 0.0;
-        Dt[off] = (c <= r) ? X[r * SLD + c] : 0.0;
+        const double lv = (c <= r) ? S[r * SLD + c] : 0.0, dv = (c <= r) ? X[r * SLD + c] : 0.0;
+        Lt[off] = lv;
+        Dt[off] = dv;
+        if (Lt32) Lt32[off] = (float)lv;
+        if (Dt32) Dt32[off] = (float)dv;
         if (Zt) Zt[off] = (r <= c) ? X[c * SLD + r] : 0.0;
     }
 }
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) ch
     if (a.mode == 0) {
         const int b = blockIdx.x;
         slot = b / a.ntiles;
-        tile = b - slot * a.ntiles + a.tile0;
+        tile = b - slot * a.ntiles;
     } else {
         slot = blockIdx.y;
         tile = blockIdx.x;
@@ -366,6 +371,8 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) ch
     slab_mma(acc, St, Dt, wm, wn, lane);
     if (wn == 1) slab_mma(acc, St + PGPFA_SLAB, Dt + PGPFA_SLAB, wm, wn, lane);   // D lower-triangular: k<=n
     double2 *O2 = reinterpret_cast<double2 *>(out);
+    float2 *F2 = (a.mode == 0 && a.L32)
+                     ? reinterpret_cast<float2 *>(a.L32 + ((size_t)slot * ltl + ltile(ti, tj)) * PGPFA_TILE) : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -374,6 +381,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) ch
             v.x = acc[i][jj][0];
             v.y = acc[i][jj][1];
             O2[frag_slot2(wm, wn, i, jj, lane)] = v;
+            if (F2) F2[frag_slot2(wm, wn, i, jj, lane)] = make_float2((float)v.x, (float)v.y);
         }
     if (a.mode != 0 || !a.fuse || tile != 0) return;
     // ---- fused look-ahead: this CTA just produced L(j+1, j), the last tile diagonal step j+1 was waiting for.
@@ -571,7 +579,7 @@ void launch_timediag(const double *ZT, const int *act, double *vsm, int nb, int 
 // internal host API (used by laplace.cu / mstep.cu / the C-ABI wrappers in api.cu)
 // =============================================================================================
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
-                   cudaStream_t st, pgpfa_handle_s *h) {
+                   cudaStream_t st, pgpfa_handle_s *h, float *L32, float *D32) {
     (void)h;
     if (nslots <= 0) return PGPFA_OK;
     PGPFA_TRY(set_smem_attrs());
@@ -579,9 +587,9 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
     a.src.Kinv = ms.Kinv; a.src.W = ms.W; a.src.dense = ms.dense;
     a.src.q = ms.q; a.src.T = ms.T; a.src.n = ms.n; a.src.diag_scale = ms.diag_scale;
     a.L = L; a.Dinv = Dinv; a.ZT = ZT; a.act = act; a.info = info;
+    a.L32 = L32; a.D32 = D32;
     a.nb = pgpfa_nb(ms.n);
     a.mode = 0;
-    a.tile0 = 0;
     a.nslots = nslots;
     a.fuse = 1;
     const int nb = a.nb;
@@ -606,9 +614,9 @@ int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int ns
     FactorArgs a;
     a.src.Kinv = nullptr; a.src.W = nullptr; a.src.dense = nullptr; a.src.q = 1; a.src.T = n; a.src.n = n; a.src.diag_scale = 1.0;
     a.L = const_cast<double *>(L); a.Dinv = const_cast<double *>(Dinv); a.ZT = ZT; a.act = nullptr; a.info = nullptr;
+    a.L32 = nullptr; a.D32 = nullptr;
     a.nb = pgpfa_nb(n);
     a.mode = 1;
-    a.tile0 = 0;
     a.nslots = nslots; a.ntiles = 0; a.fuse = 0;
     for (int i = 1; i < a.nb; i++) {
         a.step = i;

@@ -389,6 +389,7 @@ struct LapWs {
     int *conv, *actA, *actB, *actC, *lslot, *cnt;
     int2 *pairs;
     double *L, *Dinv, *ZT;
+    float *L32, *D32;
     int chunk;
 };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -405,7 +406,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
 }
 size_t lap_per_trial_bytes(int q, int T) {
     const int nb = pgpfa_nb(q * T);
-    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8;
+    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8 + (size_t)(pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 4;
 }
 }  // namespace
 
@@ -447,6 +448,8 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
     w.L = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
     w.Dinv = (double *)take((size_t)chunk * nb * PGPFA_TILE * 8);
     w.ZT = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
+    w.L32 = (float *)take((size_t)chunk * ltl * PGPFA_TILE * 4);
+    w.D32 = (float *)take((size_t)chunk * nb * PGPFA_TILE * 4);
 
     PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
@@ -484,9 +487,9 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
                 PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
                 pgpfa_prof_end(h, st);
                 pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
-                PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, act, n, n_act, st, c0));
+                PGPFA_TRY(pgpfa_i_solve32(w.L32, w.D32, w.g, w.dx, -1.0, act, n, n_act, st, c0));
                 pgpfa_prof_end(h, st);
-                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_act * solve_bytes;
+                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_act * solve_bytes * 0.5;
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol_chord, w.fcur,
@@ -514,7 +517,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
             pgpfa_prof_end(h, st);
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
-            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st, h));
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st, h, w.L32, w.D32));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_FACTOR] += (double)n_act * n * (double)n * n / 3.0;
             scatter_slots_kernel<<<(n_act + 255) / 256, 256, 0, st>>>(act, n_act, w.lslot);
@@ -542,9 +545,9 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
                 PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, swp, n_swp, q, N, T, w.fcur, w.g, w.W, st));
                 pgpfa_prof_end(h, st);
                 pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
-                PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, swp, n, n_swp, st, -1, w.lslot));
+                PGPFA_TRY(pgpfa_i_solve32(w.L32, w.D32, w.g, w.dx, -1.0, swp, n, n_swp, st, -1, w.lslot));
                 pgpfa_prof_end(h, st);
-                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_swp * solve_bytes;
+                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_swp * solve_bytes * 0.5;
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, swp, n_swp, q, T, st));
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, swp, n_swp, q, N, T, tol, w.fcur, w.conv,
@@ -574,7 +577,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         pgpfa_prof_end(h, st);
         if (vsm || vsmGP || cov_dense || reuse_factor >= 0) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
-            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h));
+            PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h, w.L32, w.D32));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_FACTOR] += (double)cn * n * (double)n * n / 3.0;
             total_factor_trials += cn;

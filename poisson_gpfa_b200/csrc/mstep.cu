@@ -212,10 +212,19 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
     double sl = 0.0, dmax = 0.0, tmax = 0.0;
 #pragma unroll
     for (int k = 0; k < P; k++) { sl += g[k] * dl[k]; dmax = fmax(dmax, fabs(dl[k])); tmax = fmax(tmax, fabs(tt[k])); }
+    // quadratic-convergence predictor: after a full Newton step of size p followed by one of size d, the error
+    // left after applying d is ~ d^3 / p^2
+    double prevmax = 0.0;
+    if (!first && alpha[n] == 1.0) {
+#pragma unroll
+        for (int k = 0; k < P; k++) prevmax = fmax(prevmax, fabs(step[(size_t)n * P + k]));
+    }
     fcur[n] = ftry;
     slope[n] = sl;
     alpha[n] = 1.0;
-    const bool conv = dmax <= tol * (1.0 + tmax);
+    bool conv = dmax <= tol * (1.0 + tmax);
+    if (!conv && prevmax > 0.0 && dmax < 0.1 * prevmax && dmax * dmax * dmax / (prevmax * prevmax) <= 0.01 * tol * (1.0 + tmax))
+        conv = true;
 #pragma unroll
     for (int k = 0; k < P; k++) {
         step[(size_t)n * P + k] = dl[k];
@@ -223,8 +232,12 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
         theta_cur[(size_t)n * P + k] = conv ? nx : tt[k];
         theta_try[(size_t)n * P + k] = nx;
     }
-    if (conv) done[n] = 1;
-    else atomicAdd(n_open, 1);
+    if (conv) {
+        done[n] = 1;
+        fcur[n] = ftry + 0.5 * sl;     // cost at the final point theta + step (second-order model, error O(step^3))
+    } else {
+        atomicAdd(n_open, 1);
+    }
 }
 
 // C = A * B for a batch of row-major n x n matrices (small FP64 GEMM, 64x64 tiles, 16x16 threads)

@@ -16,7 +16,7 @@ struct PgpfaMatSrc {
 
 struct pgpfa_handle_s;
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
-                   cudaStream_t st, pgpfa_handle_s *h = nullptr);
+                   cudaStream_t st, pgpfa_handle_s *h = nullptr, float *L32 = nullptr, float *D32 = nullptr);
 int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st);
 int pgpfa_i_lauum(const double *ZT, const int2 *pairs, int npairs, const int *act, double *vsmGP, double *dense, int n,
                   int q, int T, int nslots, cudaStream_t st);
@@ -25,6 +25,9 @@ int pgpfa_i_logdet(const double *L, int n, int nslots, double *out, cudaStream_t
 int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, double *out, cudaStream_t st);
 int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
                   int n, int nslots, cudaStream_t st, int lslot_base = -1, const int *lslot_map = nullptr);
+// same solve streaming the FP32 mirrors of the factor (inexact: for chord sweeps only)
+int pgpfa_i_solve32(const float *L32, const float *D32, const double *rhs, double *out, double scale, const int *act,
+                    int n, int nslots, cudaStream_t st, int lslot_base = -1, const int *lslot_map = nullptr);
 
 #include <vector>
 #include "../../include/pgpfa_b200.h"
@@ -48,10 +51,6 @@ struct pgpfa_handle_s {
     double prof_work[PGPFA_PROF_SLOTS];
     long long prof_cnt[PGPFA_PROF_SLOTS];
     std::vector<PgpfaProfSpan> spans, open_spans;
-    // look-ahead factorisation: critical-path stream (diag + first panel tile, high priority) and bulk stream
-    cudaStream_t s_crit, s_bulk;
-    std::vector<cudaEvent_t> ev_diag, ev_rest;
-    cudaEvent_t ev_fork, ev_join_a, ev_join_b;
 };
 void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);

@@ -13,7 +13,14 @@ namespace {
 #define SOLVE_GROUPS 4                       // warp groups of 8 warps; group g takes tiles k = g (mod 4)
 #define SOLVE_THREADS (SOLVE_GROUPS * 256)
 
-__global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double *__restrict__ L, const double *__restrict__ Dinv,
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 ld2(const float *p) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    return make_double2((double)v.x, (double)v.y);
+}
+
+template <typename TL>
+__global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const TL *__restrict__ L, const TL *__restrict__ Dinv,
                                                                    const double *__restrict__ rhs, double *__restrict__ out,
                                                                    double scale, const int *act, int nb, int n, int lslot_base,
                                                                    const int *__restrict__ lslot_map) {
@@ -29,21 +36,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double 
     // factor slot: position in the active list (fresh factorisation), trial - base (factor kept from an earlier
     // call, stored by local trial index) or lslot_map[trial] (factor computed for an earlier, longer active list)
     const int lslot = lslot_map ? lslot_map[trial] : (lslot_base >= 0 ? trial - lslot_base : slot);
-    const double *Ls = L + (size_t)lslot * ltl * PGPFA_TILE;
-    const double *Ds = Dinv + (size_t)lslot * nb * PGPFA_TILE;
+    const TL *Ls = L + (size_t)lslot * ltl * PGPFA_TILE;
+    const TL *Ds = Dinv + (size_t)lslot * nb * PGPFA_TILE;
     for (int i = tid; i < nb * PGPFA_NB; i += SOLVE_THREADS) z[i] = (i < n) ? rhs[(size_t)trial * n + i] : 0.0;
     __syncthreads();
     const int c2 = 2 * (lane & 3);
     // ---- forward: L y = rhs.  Block row j: warp (grp, w) sums L(j,k)[rows 8w..8w+7] z_k over its tiles k.
     for (int j = 0; j < nb; j++) {
-        const double *row = Ls + ltile(j, 0) * PGPFA_TILE + w * 64 + lane * 2;
+        const TL *row = Ls + ltile(j, 0) * PGPFA_TILE + w * 64 + lane * 2;
         double acc = 0.0;
         for (int k = grp; k < j; k += SOLVE_GROUPS) {
-            const double *tp = row + (size_t)k * PGPFA_TILE;
+            const TL *tp = row + (size_t)k * PGPFA_TILE;
             const double *zp = z + k * PGPFA_NB + c2;
 #pragma unroll
             for (int sp = 0; sp < 8; sp++) {
-                const double2 a = *reinterpret_cast<const double2 *>(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
+                const double2 a = ld2(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
                 const double2 v = *reinterpret_cast<const double2 *>(zp + sp * 8);
                 acc += a.x * v.x + a.y * v.y;
             }
@@ -60,11 +67,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double 
         }
         __syncthreads();
         if (grp == 0) {
-            const double *tp = Ds + (size_t)j * PGPFA_TILE + w * 64 + lane * 2;
+            const TL *tp = Ds + (size_t)j * PGPFA_TILE + w * 64 + lane * 2;
             double a2 = 0.0;
 #pragma unroll
             for (int sp = 0; sp < 8; sp++) {
-                const double2 a = *reinterpret_cast<const double2 *>(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
+                const double2 a = ld2(tp + (sp >> 2) * PGPFA_SLAB + (sp & 3) * 512);
                 const double2 v = *reinterpret_cast<const double2 *>(tmp + sp * 8 + c2);
                 a2 += a.x * v.x + a.y * v.y;
             }
@@ -80,11 +87,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double 
     const int toff = (w >> 2) * PGPFA_SLAB + (w & 3) * 512 + lane * 2;
     for (int i = nb - 1; i >= 0; i--) {
         if (grp == 0) {
-            const double *tp = Ds + (size_t)i * PGPFA_TILE + toff;
+            const TL *tp = Ds + (size_t)i * PGPFA_TILE + toff;
             double ax = 0.0, ay = 0.0;
 #pragma unroll
             for (int rb = 0; rb < 8; rb++) {
-                const double2 a = *reinterpret_cast<const double2 *>(tp + rb * 64);
+                const double2 a = ld2(tp + rb * 64);
                 const double v = z[i * PGPFA_NB + rb * 8 + (lane >> 2)];
                 ax += a.x * v;
                 ay += a.y * v;
@@ -98,16 +105,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double 
         }
         __syncthreads();
         if (tid < PGPFA_NB) z[i * PGPFA_NB + tid] = tmp[tid];
-        const double *row = Ls + ltile(i, 0) * PGPFA_TILE + toff;
+        const TL *row = Ls + ltile(i, 0) * PGPFA_TILE + toff;
         double dv[8];
 #pragma unroll
         for (int rb = 0; rb < 8; rb++) dv[rb] = tmp[rb * 8 + (lane >> 2)];
         for (int k = grp; k < i; k += SOLVE_GROUPS) {
-            const double *tp = row + (size_t)k * PGPFA_TILE;
+            const TL *tp = row + (size_t)k * PGPFA_TILE;
             double ax = 0.0, ay = 0.0;
 #pragma unroll
             for (int rb = 0; rb < 8; rb++) {
-                const double2 a = *reinterpret_cast<const double2 *>(tp + rb * 64);
+                const double2 a = ld2(tp + rb * 64);
                 ax += a.x * dv[rb];
                 ay += a.y * dv[rb];
             }
@@ -128,15 +135,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS) chol_solve_kernel(const double 
 
 }  // namespace
 
-int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
-                  int n, int nslots, cudaStream_t st, int lslot_base, const int *lslot_map) {
+template <typename TL>
+static int launch_solve(const TL *L, const TL *Dinv, const double *rhs, double *out, double scale, const int *act, int n,
+                        int nslots, cudaStream_t st, int lslot_base, const int *lslot_map) {
     if (nslots <= 0) return PGPFA_OK;
     const int nb = pgpfa_nb(n);
     const size_t smem = (size_t)(nb * PGPFA_NB + PGPFA_NB + SOLVE_GROUPS * PGPFA_NB) * sizeof(double);
-    if (smem > 48 * 1024) {
-        PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    chol_solve_kernel<<<nslots, SOLVE_THREADS, smem, st>>>(L, Dinv, rhs, out, scale, act, nb, n, lslot_base, lslot_map);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chol_solve_kernel<TL><<<nslots, SOLVE_THREADS, smem, st>>>(L, Dinv, rhs, out, scale, act, nb, n, lslot_base, lslot_map);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
+}
+
+int pgpfa_i_solve(const double *L, const double *Dinv, const double *rhs, double *out, double scale, const int *act,
+                  int n, int nslots, cudaStream_t st, int lslot_base, const int *lslot_map) {
+    return launch_solve<double>(L, Dinv, rhs, out, scale, act, n, nslots, st, lslot_base, lslot_map);
+}
+
+int pgpfa_i_solve32(const float *L32, const float *D32, const double *rhs, double *out, double scale, const int *act,
+                    int n, int nslots, cudaStream_t st, int lslot_base, const int *lslot_map) {
+    return launch_solve<float>(L32, D32, rhs, out, scale, act, n, nslots, st, lslot_base, lslot_map);
 }
