@@ -238,11 +238,20 @@ def run_ours(args):
     except Exception:
         pass
     fp64_peak = float(peaks.get("fp64_roofline_peak_tflops", 35.4))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_factor_traffic.json")))["dram_bytes_per_factorisation"]
+        traffic = traffic * (hi - lo) / 1024.0          # captured at 1024 trials per GPU
+    except Exception:
+        pass
     fac_ms, fac_flops, fac_cnt = prof_ms[0], prof_work[0], prof_cnt[0]
     achieved = fac_flops / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "batched Cholesky (chol_diag_kernel + chol_panel_kernel, DMMA.8x8x4)",
+    roofline = {"bound": "tensor", "kernel": "batched Cholesky call (chol_diag_kernel + chol_panel_kernel launches, DMMA.8x8x4); a launch = one factorisation of all trials of the rank",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one factorisation call, "
+                                  "ncu launch list of this command (profiles/r01_factor_traffic.json), scaled to this rank's "
+                                  "trial count",
                 "peak_source": "measured cuBLAS DGEMM 8192^3 sustained on this pool (profiles/r01_fp64_peaks.json); "
                                "MEASURED_PEAKS.json has no FP64 line",
                 "algorithmic_flops_per_launch": fac_flops / max(fac_cnt, 1), "launches": int(fac_cnt),

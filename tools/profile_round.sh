@@ -1,13 +1,12 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-# launch list of the bench command (every kernel, device time; cold-cache & serialised: compare shares)
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
-    python bench.py --steps 1 --warmup 3 --profile-mode > gpurun_out/bench_under_ncu.json 2> gpurun_out/ncu_bench.err
+# launch list of the bench command (every kernel: device time + DRAM bytes; cold-cache & serialised: compare shares)
+timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 3 --profile-mode \
+    > gpurun_out/bench_under_ncu.json 2> gpurun_out/ncu_bench.err
 wc -l gpurun_out/launches_bench.csv
-# full capture of the dominant kernel (panel) and the diagonal kernel, mid-factorisation steps
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chol_panel_kernel -s 20 -c 2 \
+# full capture of the dominant kernel (panel, two mid-factorisation launches of the 1024-trial factorisation)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:chol_panel_kernel -s 15 -c 2 \
     -o gpurun_out/prof_panel -f python tools/prof_factor.py > gpurun_out/ncu_panel.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chol_diag_kernel -s 20 -c 1 \
-    -o gpurun_out/prof_diag -f python tools/prof_factor.py > gpurun_out/ncu_diag.log 2>&1
 ls -la gpurun_out/*.ncu-rep
