@@ -44,6 +44,10 @@ long long pgpfa_launch_count(void);                    /* kernels launched by th
 int pgpfa_set_profiling(pgpfa_handle_t h, int on);
 int pgpfa_get_profile(pgpfa_handle_t h, double *ms_out, double *work_out, long long *count_out);
 
+/* element-wise helper: op 0 out = exp(x), op 1 out = log(x) (lambda <-> rho of funs/inference.py:227,397),
+ * op 2 out = x + a*y (scaled Newton step of funs/learning.py:890) */
+int pgpfa_map(int op, long long n, const double *x, const double *y, double a, double *out, cudaStream_t stream);
+
 /* ---- (1) GP prior: funs/util.py:599-619 makeK_big, funs/inference.py:82 inv(K_big) ---------- */
 int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double epsNoise, double *K, cudaStream_t stream);
 int pgpfa_make_K_big(const double *K, int q, int T, double *K_big, cudaStream_t stream);
@@ -94,6 +98,14 @@ int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, cons
                         double *x, int R, int q, int N, int T, double tol, int max_newton, int reuse_factor,
                         double *f_out, double *vsm, double *vsmGP, double *cov_dense, int *niter, int *info,
                         void *workspace, long long ws_bytes, int *stats_out, cudaStream_t stream);
+
+/* Leave-one-neuron-out prediction, funs/engine.py:599-644: problem p = (trial ymap[p], left-out neuron excl[p]);
+ * the posterior mode is found without that neuron (x: P x q x T, in = start, out = mode) and its rate predicted:
+ * ypred[p][t] = exp(c_n . x_p[:,t] + d_n), err[p] = sum_t (y - ypred)^2.  Workspace: pgpfa_laplace_workspace_bytes(P,..) */
+int pgpfa_loo_predict(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
+                      const int *ymap, const int *excl, double *x, int P, int q, int N, int T, double tol, int max_newton,
+                      double *ypred, double *err, int *niter, int *info, void *workspace, long long ws_bytes,
+                      int *stats_out, cudaStream_t stream);
 
 /* ---- (3) dual variational E-step: funs/inference.py:188-432 ------------------------------------ */
 long long pgpfa_dualvi_workspace_bytes(int R, int q, int T, int chunk);

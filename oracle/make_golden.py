@@ -72,10 +72,13 @@ def em_case(ref, name, ds, ip, n_iter, q, N, T):
             out['it%d_new_d' % it] = params['d']
             out['it%d_new_tau' % it] = params['tau']
             out['it%d_cd_cost' % it] = det['Cd']
-    # stock tolerances, free-running (what a user of the reference gets)
+    # stock tolerances, free-running (what a user of the reference gets), with leave-one-out prediction on the
+    # smaller cases (R*N scipy fmin_ncg solves)
     with rh.quiet():
         fit = ref.engine.PPGPFAfit(experiment=ds, initParams=copy.deepcopy(ip), inferenceMethod='laplace',
-                                   EMmode='Batch', maxEMiter=n_iter)
+                                   EMmode='Batch', maxEMiter=n_iter, getPredictionErr=True)
+    out['stock_y_pred_mode'] = fit.y_pred_mode
+    out['stock_pred_err_mode'] = fit.pred_err_mode
     out['stock_C'] = fit.optimParams['C']
     out['stock_d'] = fit.optimParams['d']
     out['stock_tau'] = fit.optimParams['tau']

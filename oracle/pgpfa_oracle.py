@@ -230,6 +230,24 @@ def laplace_struct(ys, params, T, binSize, x0s=None, tol=1e-13, want_cov=True):
     return res, -tot / len(ys), optim, iters
 
 
+def leave_one_out_struct(ys, params, T, binSize, tol=1e-13):
+    """funs/engine.py:599-644 with exact Newton: y_pred[r][n] = exp(c_n x_mode(-n) + d_n), summed squared error."""
+    C = np.asarray(params['C'], dtype=np.float64)
+    d = np.ravel(np.asarray(params['d'], dtype=np.float64))
+    N, q = C.shape
+    K = make_K(params['tau'], T, binSize)
+    Kinv = np.stack([np.linalg.inv(K[k]) for k in range(q)])
+    pred = np.zeros((len(ys), N, T))
+    err = 0.0
+    for r, y in enumerate(ys):
+        for n in range(N):
+            keep = np.arange(N) != n
+            x, _, _ = newton_mode_struct(y[keep], C[keep], d[keep], Kinv, None, tol)
+            pred[r, n] = np.exp(C[n] @ x + d[n])
+            err += ((y[n] - pred[r, n]) ** 2).sum()
+    return pred, err
+
+
 # ----------------------------------------------------------------------------
 # Dual variational inference
 # ----------------------------------------------------------------------------

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pgpfa_launch_count": (c_ll, []),
     "pgpfa_set_profiling": (c_int, [c_void_p, c_int]),
     "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
+    "pgpfa_map": (c_int, [c_int, c_ll, P, P, c_dbl, P, P]),
     "pgpfa_make_K": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P]),
     "pgpfa_make_K_big": (c_int, [P, c_int, c_int, P, P]),
     "pgpfa_make_K_gamma": (c_int, [P, c_int, c_int, c_dbl, P, P, P]),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "pgpfa_laplace_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "pgpfa_laplace_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int,
                                     P, P, P, P, P, P, P, c_ll, P, P]),
+    "pgpfa_loo_predict": (c_int, [c_void_p, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int, P, P, P, P, P,
+                                  c_ll, P, P]),
     "pgpfa_dualvi_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "pgpfa_dualvi_eval": (c_int, [c_void_p, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_ll, P]),
     "pgpfa_dualvi_solve": (c_int, [c_void_p, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_int,

@@ -151,7 +151,7 @@ class DeviceTrials:
                 call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
                      ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open),
                      stream())
-                th_cur = theta0 + step_size * step
+                th_cur = kn.emap("axpy", theta0, step, step_size)
                 break
             call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
                  ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol),

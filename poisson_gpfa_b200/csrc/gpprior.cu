@@ -61,6 +61,18 @@ __global__ void hessian_dense_kernel(const double *__restrict__ Kinv, const doub
     }
 }
 
+// small element-wise helpers so that no arithmetic has to go through torch on the host side
+__global__ void map_kernel(int op, size_t n, const double *__restrict__ x, const double *__restrict__ y, double a,
+                           double *__restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v;
+    if (op == 0) v = exp(x[i]);
+    else if (op == 1) v = log(x[i]);
+    else v = x[i] + a * y[i];
+    out[i] = v;
+}
+
 struct InvWs { double *L, *Dinv, *ZT; int2 *pairs; };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -224,4 +236,12 @@ extern "C" int pgpfa_pautosum(const double *vsmGP, const double *m, int R, int q
                               cudaStream_t st) {
     if (!vsmGP || !m || !P || R <= 0 || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
     return pgpfa_i_pautosum(vsmGP, m, R, q, T, accumulate, P, st);
+}
+
+/* op 0: out = exp(x); op 1: out = log(x); op 2: out = x + a*y   (n doubles) */
+extern "C" int pgpfa_map(int op, long long n, const double *x, const double *y, double a, double *out, cudaStream_t st) {
+    if (n <= 0 || !x || !out || op < 0 || op > 2 || (op == 2 && !y)) return PGPFA_ERR_ARG;
+    map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, (size_t)n, x, y, a, out);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
 }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
                                                            const double *__restrict__ d, const double *__restrict__ off,
                                                            const int *act, int N, int T,
                                                            double *__restrict__ f, double *__restrict__ g,
-                                                           double *__restrict__ W) {
+                                                           double *__restrict__ W, LooMap loo) {
     extern __shared__ double sm[];
     double *Cs = sm;             // N*Q
     double *ds = sm + N * Q;     // N
@@ -75,9 +75,13 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
         for (int k = 0; k < Q; k++) { xk[k] = x[((size_t)trial * Q + k) * T + t]; gk[k] = 0.0; }
 #pragma unroll
         for (int i = 0; i < Q * (Q + 1) / 2; i++) w[i] = 0.0;
-        const double *yp = y + (size_t)trial * N * T + t;
+        // leave-one-neuron-out problems share the counts of their trial and skip one neuron
+        const int yrow = loo.ymap ? loo.ymap[trial] : trial;
+        const int skip = loo.excl ? loo.excl[trial] : -1;
+        const double *yp = y + (size_t)yrow * N * T + t;
         const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
         for (int n = 0; n < N; n++) {
+            if (n == skip) continue;
             double h = ds[n];
 #pragma unroll
             for (int k = 0; k < Q; k++) h += Cs[n * Q + k] * xk[k];
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
     const double *__restrict__ d, const double *__restrict__ off, const int *act, int N, int T, double tol,
     double *__restrict__ fcur, int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen,
-    int chord_it) {
+    int chord_it, LooMap loo) {
     extern __shared__ double sm[];
     double *Cs = sm;
     double *ds = sm + N * Q;
@@ -154,9 +158,12 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
             double xk[Q], dk[Q];
 #pragma unroll
             for (int k = 0; k < Q; k++) { xk[k] = x[base + (size_t)k * T + t]; dk[k] = dx[base + (size_t)k * T + t]; }
-            const double *yp = y + (size_t)trial * N * T + t;
+            const int yrow = loo.ymap ? loo.ymap[trial] : trial;
+            const int skip = loo.excl ? loo.excl[trial] : -1;
+            const double *yp = y + (size_t)yrow * N * T + t;
             const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
             for (int n = 0; n < N; n++) {
+                if (n == skip) continue;
                 double h = ds[n], dh = 0.0;
 #pragma unroll
                 for (int k = 0; k < Q; k++) { h += Cs[n * Q + k] * xk[k]; dh += Cs[n * Q + k] * dk[k]; }
@@ -294,11 +301,11 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
 
 template <int Q>
 int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const double *off,
-                const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st) {
+                const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st, LooMap loo) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W);
+    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W, loo);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -306,11 +313,11 @@ int launch_eval(const double *x, const double *Kx, const double *y, const double
 template <int Q>
 int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
                       const double *C, const double *d, const double *off, const int *act, int nslots, int N, int T, double tol,
-                      double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st) {
+                      double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st, LooMap loo) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it);
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it, loo);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -331,10 +338,10 @@ int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const 
 
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st, const double *off) {
+                         cudaStream_t st, const double *off, LooMap loo) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, off, act, nslots, N, T, f, g, W, st);
+#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, off, act, nslots, N, T, f, g, W, st, loo);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -344,10 +351,10 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st, const double *off) {
+                       cudaStream_t st, const double *off, LooMap loo) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st);
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st, loo);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -417,11 +424,11 @@ extern "C" long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chun
     return (long long)(lap_fixed_bytes(R, q, T, (int)pgpfa_ltiles(nb)) + (size_t)chunk * lap_per_trial_bytes(q, T) + 4096);
 }
 
-extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d,
-                                   const double *Kinv, double *x, int R, int q, int N, int T, double tol,
-                                   int max_newton, int reuse_factor, double *f_out, double *vsm, double *vsmGP,
-                                   double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
-                                   int *stats_out, cudaStream_t st) {
+static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C, const double *d,
+                              const double *Kinv, double *x, int R, int q, int N, int T, double tol,
+                              int max_newton, int reuse_factor, double *f_out, double *vsm, double *vsmGP,
+                              double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
+                              int *stats_out, cudaStream_t st, LooMap loo, bool posterior_pass) {
     if (!h || !y || !C || !d || !Kinv || !x || !f_out || !niter || !info || !workspace) return PGPFA_ERR_ARG;
     if (R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0 || max_newton <= 0) return PGPFA_ERR_ARG;
     const int n = q * T, nb = pgpfa_nb(n);
@@ -484,7 +491,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             for (int it = 0; it < 6 && n_act > 0; it++) {
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
-                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
+                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
                 pgpfa_prof_end(h, st);
                 pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
                 PGPFA_TRY(pgpfa_i_solve32(w.L32, w.D32, w.g, w.dx, -1.0, act, n, n_act, st, c0));
@@ -493,7 +500,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol_chord, w.fcur,
-                                             w.conv, niter, w.steplen, it, st));
+                                             w.conv, niter, w.steplen, it, st, nullptr, loo));
                 pgpfa_prof_end(h, st);
                 compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, act_next, w.cnt);
                 PGPFA_LAUNCH_CHECK();
@@ -514,7 +521,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         for (int it = 0; it < max_newton && n_act > 0; it++) {
             pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
-            PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st));
+            PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
             pgpfa_prof_end(h, st);
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, nullptr, act, info, n_act, st, h, w.L32, w.D32));
@@ -529,7 +536,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
-                                         niter, w.steplen, -1 - it, st));
+                                         niter, w.steplen, -1 - it, st, nullptr, loo));
             pgpfa_prof_end(h, st);
             total_factor_trials += n_act;
             if (it + 1 > max_it_used) max_it_used = it + 1;
@@ -542,7 +549,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
             for (int cs = 0; cs < 8 && n_swp > 0; cs++) {
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, swp, n_swp, q, T, st));
-                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, swp, n_swp, q, N, T, w.fcur, w.g, w.W, st));
+                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, swp, n_swp, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
                 pgpfa_prof_end(h, st);
                 pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
                 PGPFA_TRY(pgpfa_i_solve32(w.L32, w.D32, w.g, w.dx, -1.0, swp, n, n_swp, st, -1, w.lslot));
@@ -551,7 +558,7 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, swp, n_swp, q, T, st));
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, swp, n_swp, q, N, T, tol, w.fcur, w.conv,
-                                             niter, w.steplen, 1000 + cs, st));
+                                             niter, w.steplen, 1000 + cs, st, nullptr, loo));
                 pgpfa_prof_end(h, st);
                 compact_active_kernel<<<1, 1024, 0, st>>>(swp, n_swp, w.conv, 1, swp_next, w.cnt);
                 PGPFA_LAUNCH_CHECK();
@@ -573,9 +580,9 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         PGPFA_LAUNCH_CHECK();
         pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
         PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, w.actA, cn, q, T, st));
-        PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, w.actA, cn, q, N, T, f_out, w.g, w.W, st));
+        PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, w.actA, cn, q, N, T, f_out, w.g, w.W, st, nullptr, loo));
         pgpfa_prof_end(h, st);
-        if (vsm || vsmGP || cov_dense || reuse_factor >= 0) {
+        if (posterior_pass) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h, w.L32, w.D32));
             pgpfa_prof_end(h, st);
@@ -612,4 +619,60 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
         stats_out[7] = fresh_sweeps;
     }
     return not_converged ? PGPFA_ERR_NOT_CONVERGED : PGPFA_OK;
+}
+
+extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d,
+                                   const double *Kinv, double *x, int R, int q, int N, int T, double tol,
+                                   int max_newton, int reuse_factor, double *f_out, double *vsm, double *vsmGP,
+                                   double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
+                                   int *stats_out, cudaStream_t st) {
+    LooMap loo;
+    loo.ymap = nullptr; loo.excl = nullptr;
+    return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, reuse_factor, f_out, vsm, vsmGP, cov_dense,
+                              niter, info, workspace, ws_bytes, stats_out, st, loo, true);
+}
+
+// y_pred[p][t] = exp(c_n . x_p[:,t] + d_n) for the left-out neuron n = excl[p]; err[p] = sum_t (y - y_pred)^2
+template <int Q>
+__global__ void __launch_bounds__(256) loo_predict_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                          const double *__restrict__ C, const double *__restrict__ d,
+                                                          const int *__restrict__ ymap, const int *__restrict__ excl,
+                                                          int N, int T, double *__restrict__ ypred, double *__restrict__ err) {
+    __shared__ double red[32];
+    const int p = blockIdx.x, n = excl[p];
+    double e = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double h = d[n];
+#pragma unroll
+        for (int k = 0; k < Q; k++) h += C[n * Q + k] * x[((size_t)p * Q + k) * T + t];
+        const double yp = exp(h);
+        ypred[(size_t)p * T + t] = yp;
+        const double r = y[((size_t)ymap[p] * N + n) * T + t] - yp;
+        e += r * r;
+    }
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) err[p] = e;
+}
+
+// Leave-one-neuron-out prediction (funs/engine.py:599-644): problem p = (trial ymap[p], left-out neuron excl[p]).
+// Finds the posterior mode without that neuron (x in/out, P x q x T, cold start = zeros) and predicts its rate.
+extern "C" int pgpfa_loo_predict(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
+                                 const int *ymap, const int *excl, double *x, int P, int q, int N, int T, double tol,
+                                 int max_newton, double *ypred, double *err, int *niter, int *info, void *workspace,
+                                 long long ws_bytes, int *stats_out, cudaStream_t st) {
+    if (!ymap || !excl || !ypred || !err || !workspace) return PGPFA_ERR_ARG;
+    LooMap loo;
+    loo.ymap = ymap; loo.excl = excl;
+    // f_out scratch: the first P doubles of the workspace tail are not needed afterwards -> use err as f_out
+    int rc = laplace_solve_impl(h, y, C, d, Kinv, x, P, q, N, T, tol, max_newton, 0, err, nullptr, nullptr, nullptr, niter, info,
+                                workspace, ws_bytes, stats_out, st, loo, false);
+    if (rc != PGPFA_OK && rc != PGPFA_ERR_NOT_CONVERGED) return rc;
+    switch (q) {
+#define CASE_Q(QQ) case QQ: loo_predict_kernel<QQ><<<P, 256, 0, st>>>(x, y, C, d, ymap, excl, N, T, ypred, err); break;
+        PGPFA_FOR_EACH_Q(CASE_Q)
+#undef CASE_Q
+        default: return PGPFA_ERR_ARG;
+    }
+    PGPFA_LAUNCH_CHECK();
+    return rc;
 }

@@ -56,15 +56,19 @@ void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
 void pgpfa_prof_resolve(pgpfa_handle_t h);
 
+// leave-one-neuron-out problems: problem -> row of y, problem -> excluded neuron (nullptr = ordinary trials)
+struct LooMap { const int *ymap; const int *excl; };
+static inline LooMap pgpfa_no_loo() { LooMap l; l.ymap = nullptr; l.excl = nullptr; return l; }
+
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
                         cudaStream_t st);
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st, const double *off = nullptr);
+                         cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo());
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st, const double *off = nullptr);
+                       cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo());
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);

@@ -191,7 +191,7 @@ class PPGPFAfit():
         if extractAllTraj_trueParams:
             self.extractTrajWithTrueParams(method=inferenceMethod)
         if getPredictionErr:
-            raise NotImplementedError("leave-one-neuron-out prediction is scheduled after the hot path (SURVEY.md §8f-3)")
+            self.leaveOneOutPrediction()
 
     # -------------------------------------------------------------------- post-fit helpers (host side)
     def extractTrajectories(self, method='laplace'):
@@ -241,6 +241,24 @@ class PPGPFAfit():
             self.cov_err_init_obs = nrm(E_yy_obs - E_yy_init) / nrm(E_yy_obs)
             self.JSdiv_cov_optim_obs = util.JSLogdetDiv(E_yy_opt, E_yy_obs)
             self.JSdiv_cov_init_obs = util.JSLogdetDiv(E_yy_init, E_yy_obs)
+
+    def leaveOneOutPrediction(self):
+        """funs/engine.py:599-644: for every trial and neuron, the posterior mode from the other N-1 neurons and the
+        predicted rate of the left-out one.  The reference runs R*N scipy fmin_ncg solves in a Python double loop;
+        here they are one batch of R*N Laplace problems (pgpfa_loo_predict) over this rank's trials.
+        Sets y_pred_mode (R, N, T) and pred_err_mode (sum of squared errors, all ranks)."""
+        import torch
+        from . import kernels as kn
+        trials = inference.device_trials(self.experiment, self._reducer)
+        p = inference.device_params(self.optimParams, self.T, self.binSize)
+        R, N = trials.R, trials.N
+        ymap = torch.arange(R, device="cuda", dtype=torch.int32).repeat_interleave(N).contiguous()
+        excl = torch.arange(N, device="cuda", dtype=torch.int32).repeat(R).contiguous()
+        ypred, err, _, st = kn.loo_predict(trials.y, p.C, p.d, p.Kinv, ymap, excl)
+        if st["not_converged"]:
+            raise RuntimeError("leave-one-out prediction: %d problems did not converge" % st["not_converged"])
+        self.y_pred_mode = ypred.reshape(R, N, self.T).cpu().numpy()
+        self.pred_err_mode = self._reducer.sum_scalar(float(err.sum()))
 
     def processParamResults(self):
         """funs/engine.py:545-597 (host-side bookkeeping over paramSeq; diagnostics, not hot path)."""

@@ -316,7 +316,7 @@ def dualVariational(experiment, params, optimizeLogLambda=False, prevOptimRes=No
             sel = range(trials.offset, trials.offset + trials.R) if len(prevOptimRes) == trials.R_total else range(trials.R)
             lam0 = _f64(np.stack([np.asarray(prevOptimRes[i], dtype=np.float64).reshape(trials.N, T) for i in sel]))
         if optimizeLogLambda:
-            lam0 = torch.exp(lam0)
+            lam0 = kn.emap("exp", lam0.contiguous())
         lam0 = lam0.contiguous()
     est = trials.estep_variational(p, lam0=lam0, tol=tol)
     if verbose:
@@ -326,6 +326,6 @@ def dualVariational(experiment, params, optimizeLogLambda=False, prevOptimRes=No
     post_lik = trials.post_lik(est)
     lower = trials.reducer.sum_scalar(float(est.dual.sum())) / trials.R_total
     if returnOptimRes:
-        opt = torch.log(est.lam) if optimizeLogLambda else est.lam
+        opt = kn.emap("log", est.lam) if optimizeLogLambda else est.lam
         return infRes, post_lik, lower, _TrialView(opt.reshape(trials.R, -1))
     return infRes, post_lik, lower

@@ -13,6 +13,14 @@ from ._lib import call, empty, handle, ptr, stream, workspace
 QMAX = 12
 
 
+def emap(op, x, y=None, a=0.0):
+    """Element-wise helper on the device: op 'exp', 'log', or 'axpy' (x + a*y)."""
+    code = {"exp": 0, "log": 1, "axpy": 2}[op]
+    out = torch.empty_like(x)
+    call("pgpfa_map", code, x.numel(), ptr(x), ptr(y), float(a), ptr(out), stream())
+    return out
+
+
 def make_K(tau, T, binSize, epsNoise=0.001):
     """funs/util.py:599-614 -> K (q,T,T)."""
     q = tau.numel()
@@ -239,6 +247,26 @@ def dualvi_solve(y, C, d, K, Kinv, lam0=None, tol=1e-10, max_iter=200, want_vsmG
                   ctypes.cast(stats, ctypes.c_void_p), stream(), allow=(_lib.ERR_NOT_CONVERGED,))
     res.stats = {"factorizations": stats[0], "sweeps": stats[1], "not_converged": stats[2], "chunk": stats[3]}
     return res
+
+
+def loo_predict(y, C, d, Kinv, ymap, excl, tol=1e-8, max_newton=60):
+    """Leave-one-neuron-out prediction for problems p = (trial ymap[p], neuron excl[p]) (int32 device tensors).
+    Returns (ypred (P,T), err (P), modes (P,q,T), stats)."""
+    R, N, T = y.shape
+    q = C.shape[1]
+    Pn = ymap.numel()
+    x = torch.zeros(Pn, q, T, dtype=torch.float64, device="cuda")
+    ypred, err = empty(Pn, T), empty(Pn)
+    niter, info = empty(Pn, dtype=torch.int32), empty(Pn, dtype=torch.int32)
+    full = _lib.lib.pgpfa_laplace_workspace_bytes(Pn, q, T, Pn)
+    free, _ = torch.cuda.mem_get_info()
+    nbytes = full if full <= int(free * 0.8) else max(int(free * 0.8), _lib.lib.pgpfa_laplace_workspace_bytes(Pn, q, T, 1))
+    ws = workspace(nbytes)
+    stats = (ctypes.c_int * 8)()
+    rc = call("pgpfa_loo_predict", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(ymap), ptr(excl), ptr(x), Pn, q, N, T,
+              float(tol), int(max_newton), ptr(ypred), ptr(err), ptr(niter), ptr(info), ptr(ws), ws.numel(),
+              ctypes.cast(stats, ctypes.c_void_p), stream(), allow=(_lib.ERR_NOT_CONVERGED,))
+    return ypred, err, x, {"rc": rc, "factorizations": stats[0], "max_newton_iters": stats[1], "not_converged": stats[2]}
 
 
 def pautosum(vsmGP, post_mean, out=None, accumulate=False):

@@ -205,3 +205,21 @@ def test_online_minibatch_gathers_from_resident_parent_with_Y_all():
     tr = inference.device_trials(sub)
     assert tr.R == 5 and tr.R_total == 5
     assert np.array_equal(tr.y.cpu().numpy(), ex.Y_all[sub.batchTrIdx])
+
+
+@pytest.mark.parametrize("name,q,N,T", CASES)
+def test_leave_one_out_prediction(name, q, N, T):
+    """engine.leaveOneOutPrediction (getPredictionErr=True): R*N batched Laplace problems with one neuron removed."""
+    from poisson_gpfa_b200 import engine
+    g = load_golden(name)
+    ex = Exp(g)
+    fit = engine.PPGPFAfit(experiment=ex, initParams=init_params(g), inferenceMethod='laplace', EMmode='Batch',
+                           maxEMiter=1, quiet=True)
+    fit.optimParams = {'C': g['stock_C'].copy(), 'd': g['stock_d'].copy(), 'tau': g['stock_tau'].copy()}
+    fit.leaveOneOutPrediction()
+    pred_o, err_o = po.leave_one_out_struct(list(g['Y']), fit.optimParams, T, ex.binSize)
+    assert fit.y_pred_mode.shape == (len(ex.data), N, T)
+    assert rel(fit.y_pred_mode, pred_o) <= 1e-8
+    assert abs(fit.pred_err_mode - err_o) <= 1e-10 * err_o
+    assert rel(fit.y_pred_mode, g['stock_y_pred_mode']) <= 5e-3       # reference: fmin_ncg at scipy's default tolerance
+    assert abs(fit.pred_err_mode - float(g['stock_pred_err_mode'])) <= 1e-3 * err_o
