@@ -48,6 +48,11 @@ int pgpfa_get_profile(pgpfa_handle_t h, double *ms_out, double *work_out, long l
  * op 2 out = x + a*y (scaled Newton step of funs/learning.py:890) */
 int pgpfa_map(int op, long long n, const double *x, const double *y, double a, double *out, cudaStream_t stream);
 
+/* Stevenson-style loader (funs/datamanager.py:8-54): spike times (CSR over (trial, neuron)) -> counts (R,N,T)
+ * with numpy.histogram's binning rules; ptr is int64 */
+int pgpfa_bin_spikes(const double *times, const long long *ptr, const double *t0, double dur, int R, int N, int T,
+                     double *Y, cudaStream_t stream);
+
 /* ---- (1) GP prior: funs/util.py:599-619 makeK_big, funs/inference.py:82 inv(K_big) ---------- */
 int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double epsNoise, double *K, cudaStream_t stream);
 int pgpfa_make_K_big(const double *K, int q, int T, double *K_big, cudaStream_t stream);

@@ -73,6 +73,29 @@ __global__ void map_kernel(int op, size_t n, const double *__restrict__ x, const
     out[i] = v;
 }
 
+// Spike times -> counts with numpy.histogram's edge rules (funs/datamanager.py:38-39: T equal bins over
+// [t0, t0 + dur], right edge closed, out-of-range spikes ignored).  CSR input: spikes of (trial r, neuron n) are
+// times[ptr[r*N+n] .. ptr[r*N+n+1]).
+__global__ void bin_spikes_kernel(const double *__restrict__ times, const long long *__restrict__ ptr,
+                                  const double *__restrict__ t0, double dur, int N, int T, double *__restrict__ Y) {
+    const int cell = blockIdx.x;                    // r*N + n
+    const int r = cell / N;
+    const double first = t0[r], last = t0[r] + dur;
+    const double step = (last - first) / (double)T;
+    for (long long i = ptr[cell] + threadIdx.x; i < ptr[cell + 1]; i += blockDim.x) {
+        const double x = times[i];
+        if (!(x >= first && x <= last)) continue;
+        int idx = (int)(((x - first) / (last - first)) * (double)T);
+        if (idx == T) idx = T - 1;                  // x == last edge
+        // numpy re-checks against the linspace edges (edge_k = first + k*step, last edge exact)
+        const double lo = first + (double)idx * step;
+        const double hi = (idx + 1 == T) ? last : first + (double)(idx + 1) * step;
+        if (x < lo) idx--;
+        else if (x >= hi && idx != T - 1) idx++;
+        atomicAdd(&Y[(size_t)cell * T + idx], 1.0);
+    }
+}
+
 struct InvWs { double *L, *Dinv, *ZT; int2 *pairs; };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -242,6 +265,17 @@ extern "C" int pgpfa_pautosum(const double *vsmGP, const double *m, int R, int q
 extern "C" int pgpfa_map(int op, long long n, const double *x, const double *y, double a, double *out, cudaStream_t st) {
     if (n <= 0 || !x || !out || op < 0 || op > 2 || (op == 2 && !y)) return PGPFA_ERR_ARG;
     map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, (size_t)n, x, y, a, out);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+/* Spike times -> count matrix Y (R,N,T) with numpy.histogram semantics (funs/datamanager.py:38-39).
+ * times: all spike times (s), ptr: (R*N+1) CSR offsets, t0: (R) trial start times, dur: trial duration (s). */
+extern "C" int pgpfa_bin_spikes(const double *times, const long long *ptr, const double *t0, double dur, int R, int N,
+                                int T, double *Y, cudaStream_t st) {
+    if (!ptr || !t0 || !Y || R <= 0 || N <= 0 || T <= 0 || !(dur > 0.0)) return PGPFA_ERR_ARG;
+    PGPFA_CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)R * N * T * sizeof(double), st));
+    bin_spikes_kernel<<<R * N, 64, 0, st>>>(times, ptr, t0, dur, N, T, Y);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }

@@ -21,6 +21,13 @@ def emap(op, x, y=None, a=0.0):
     return out
 
 
+def bin_spikes(times, ptr_, t0, dur, R, N, T):
+    """Spike times (float64, CSR offsets int64 over (trial, neuron)) -> counts (R,N,T), numpy.histogram rules."""
+    Y = empty(R, N, T)
+    call("pgpfa_bin_spikes", ptr(times) if times.numel() else None, ptr(ptr_), ptr(t0), float(dur), R, N, T, ptr(Y), stream())
+    return Y
+
+
 def make_K(tau, T, binSize, epsNoise=0.001):
     """funs/util.py:599-614 -> K (q,T,T)."""
     q = tau.numel()

@@ -223,3 +223,27 @@ def test_leave_one_out_prediction(name, q, N, T):
     assert abs(fit.pred_err_mode - err_o) <= 1e-10 * err_o
     assert rel(fit.y_pred_mode, g['stock_y_pred_mode']) <= 5e-3       # reference: fmin_ncg at scipy's default tolerance
     assert abs(fit.pred_err_mode - float(g['stock_pred_err_mode'])) <= 1e-3 * err_o
+
+
+def test_stevenson_style_loader_bins_like_numpy_histogram():
+    """datamanager.StevensonDataset on a schema-compatible stand-in: device binning == np.histogram, bit for bit
+    (funs/datamanager.py:38-39), including spikes exactly on bin edges and outside the window."""
+    from poisson_gpfa_b200 import datamanager, engine
+    mat = datamanager.synthetic_matdat(seed=3, numTrials=10, ydim=9, dur_s=1.6)
+    tr = mat['Subject'][0]['Trial'][0]
+    t_first = float(np.min(tr[5]['Time'][0]))
+    # adversarial spikes: exactly on edges, at the closed right end, just outside
+    tr[5]['Neuron'][0][0] = [[np.array([t_first, t_first + 0.01, t_first + 0.7, t_first + 1.4, t_first + 1.4000001,
+                                        t_first - 1e-9, t_first + 0.35]).reshape(-1, 1)]]
+    ds = datamanager.StevensonDataset(ydim=9, trialDur=1400, binSize=10, matdat=mat)
+    assert ds.numTrials == 5 and ds.T == 140 and len(ds.data) == 5 and ds.data[0]['Y'].shape == (9, 140)
+    for i, trial_id in enumerate(range(5, 10)):
+        tt = np.asarray(tr[trial_id]['Time'][0]).flatten()
+        lo = np.min(tt)
+        for yd in range(9):
+            ref = np.histogram(np.asarray(tr[trial_id]['Neuron'][0][yd][0][0]).flatten(), 140, range=(lo, lo + 1.4))[0]
+            assert np.array_equal(ds.data[i]['Y'][yd], ref), (trial_id, yd)
+    # the loaded object drives a fit like any other experiment (configs[1] path: Laplace EM on binned spike trains)
+    np.random.seed(0)
+    fit = engine.PPGPFAfit(experiment=ds, xdim=2, inferenceMethod='laplace', EMmode='Batch', maxEMiter=2, quiet=True)
+    assert len(fit.posteriorLikelihood) == 2 and np.all(np.isfinite(fit.optimParams['C']))
