@@ -53,6 +53,12 @@ int pgpfa_map(int op, long long n, const double *x, const double *y, double a, d
 int pgpfa_bin_spikes(const double *times, const long long *ptr, const double *t0, double dur, int R, int N, int T,
                      double *Y, cudaStream_t stream);
 
+/* Device-side dataset sampling (funs/util.py:733-752; statistically, not stream-, equivalent to numpy):
+ * standard normals, and Poisson counts y ~ Poisson(exp(C x + d)) */
+int pgpfa_sample_normal(double *z, long long n, unsigned long long seed, cudaStream_t stream);
+int pgpfa_sample_poisson(const double *x, const double *C, const double *d, int R, int q, int N, int T,
+                         unsigned long long seed, double *y, cudaStream_t stream);
+
 /* ---- (1) GP prior: funs/util.py:599-619 makeK_big, funs/inference.py:82 inv(K_big) ---------- */
 int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double epsNoise, double *K, cudaStream_t stream);
 int pgpfa_make_K_big(const double *K, int q, int T, double *K_big, cudaStream_t stream);

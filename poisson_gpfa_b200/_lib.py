@@ -27,6 +27,8 @@ SIGNATURES = {
     "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
     "pgpfa_map": (c_int, [c_int, c_ll, P, P, c_dbl, P, P]),
     "pgpfa_bin_spikes": (c_int, [P, P, P, c_dbl, c_int, c_int, c_int, P, P]),
+    "pgpfa_sample_normal": (c_int, [P, c_ll, ctypes.c_ulonglong, P]),
+    "pgpfa_sample_poisson": (c_int, [P, P, P, c_int, c_int, c_int, c_int, ctypes.c_ulonglong, P, P]),
     "pgpfa_make_K": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P]),
     "pgpfa_make_K_big": (c_int, [P, c_int, c_int, P, P]),
     "pgpfa_make_K_gamma": (c_int, [P, c_int, c_int, c_dbl, P, P, P]),

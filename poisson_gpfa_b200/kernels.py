@@ -28,6 +28,22 @@ def bin_spikes(times, ptr_, t0, dur, R, N, T):
     return Y
 
 
+def sample_dataset(C, d, tau, R, T, binSize, seed, epsNoise=0.001):
+    """Draw X (R,q,T) ~ GP(0,K(tau)) and Y (R,N,T) ~ Poisson(exp(CX+d)) on the device (funs/util.py:733-752)."""
+    q = tau.numel()
+    N = C.shape[0]
+    K = make_K(tau, T, binSize, epsNoise)
+    L, D, _, info = potrf_dense(K, want_zt=False)
+    Lt = tiles_to_dense(L, T).transpose(1, 2).contiguous()          # prior_apply multiplies by the transpose
+    z = empty(R, q, T)
+    call("pgpfa_sample_normal", ptr(z), z.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, stream())
+    X = prior_apply(Lt, z)                                          # x_k = chol(K_k) z_k
+    Y = empty(R, N, T)
+    call("pgpfa_sample_poisson", ptr(X), ptr(C), ptr(d), R, q, N, T, (int(seed) * 0x9E3779B97F4A7C15 + 1) & 0xFFFFFFFFFFFFFFFF,
+         ptr(Y), stream())
+    return X, Y
+
+
 def make_K(tau, T, binSize, epsNoise=0.001):
     """funs/util.py:599-614 -> K (q,T,T)."""
     q = tau.numel()

@@ -129,3 +129,30 @@ def test_full_shape_properties():
     # (5) determinism: the same call twice gives identical bits
     est4 = trials.estep_laplace(p, reuse_factor=False)
     assert torch.equal(est4.x, est.x) and torch.equal(est4.vsmGP, est.vsmGP)
+
+
+def test_device_sampling_statistics():
+    """Device-side dataset sampling (funs/util.py:733-752): not stream-compatible with numpy, so check the
+    distributions: latent covariance ~ K(tau), counts ~ Poisson(exp(CX+d)) (mean and Fano factor)."""
+    from poisson_gpfa_b200 import kernels as kn, util
+    q, N, T, R = 3, 8, 40, 4000
+    ex = util.simulate_on_device(11, q, N, R, T, binSize=10, dOffset=0.0)
+    X = np.stack([t['X'] for t in ex.data])
+    Y = ex.Y_all
+    assert Y.shape == (R, N, T) and np.all(Y >= 0) and np.all(Y == np.round(Y))
+    K = po.make_K(ex.params['tau'], T, 10)
+    for k in range(q):
+        emp = np.einsum('rs,rt->st', X[:, k], X[:, k]) / R
+        assert np.abs(emp - K[k]).max() <= 6.0 / np.sqrt(R)                 # entries have sd <= sqrt(2/R)
+    assert abs(X.mean()) <= 5.0 / np.sqrt(R * q * T) * 3
+    rate = np.exp(np.einsum('nk,rkt->rnt', ex.params['C'], X) + ex.params['d'][None, :, None])
+    resid = (Y - rate)
+    zscore = resid.sum() / np.sqrt(rate.sum())
+    assert abs(zscore) <= 5.0
+    fano = (resid ** 2).sum() / rate.sum()                                   # Poisson: E (y-lam)^2 = lam
+    assert abs(fano - 1.0) <= 0.02
+    # reproducible for a fixed seed, different for another
+    ex2 = util.simulate_on_device(11, q, N, 50, T, binSize=10, dOffset=0.0)
+    ex3 = util.simulate_on_device(12, q, N, 50, T, binSize=10, dOffset=0.0)
+    assert np.array_equal(ex2.Y_all, util.simulate_on_device(11, q, N, 50, T, binSize=10, dOffset=0.0).Y_all)
+    assert not np.array_equal(ex2.Y_all, ex3.Y_all)
