@@ -210,35 +210,6 @@ __global__ void negate_kernel(double *p, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = -p[i];
 }
-__global__ void iota2_kernel(int *p, int n, int start) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = start + i;
-}
-__global__ void __launch_bounds__(1024) compact2_kernel(const int *__restrict__ act_in, int n_in, const int *__restrict__ conv,
-                                                        int *__restrict__ act_out, int *__restrict__ n_out) {
-    __shared__ int wsum[32];
-    __shared__ int running;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) running = 0;
-    __syncthreads();
-    for (int b = 0; b < n_in; b += 1024) {
-        const int i = b + tid;
-        int trial = -1, keep = 0;
-        if (i < n_in) { trial = act_in[i]; keep = conv[trial] ? 0 : 1; }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        const int wpre = __popc(m & ((1u << lane) - 1));
-        if (lane == 0) wsum[warp] = __popc(m);
-        __syncthreads();
-        int off = running;
-        for (int w = 0; w < warp; w++) off += wsum[w];
-        if (keep) act_out[off + wpre] = trial;
-        __syncthreads();
-        if (tid == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += wsum[w]; running += tot; }
-        __syncthreads();
-    }
-    if (tid == 0) *n_out = running;
-}
-
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t smem_cd(int N, int q) { return (size_t)(N * q + N) * sizeof(double); }
 
@@ -337,8 +308,7 @@ extern "C" int pgpfa_dualvi_eval(pgpfa_handle_t h, const double *lam, const doub
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0 + 1e-6;
     for (int c0 = 0; c0 < R; c0 += chunk) {
         const int cn = (R - c0) < chunk ? (R - c0) : chunk;
-        iota2_kernel<<<(cn + 255) / 256, 256, 0, st>>>(w.actA, cn, c0);
-        PGPFA_LAUNCH_CHECK();
+        PGPFA_TRY(pgpfa_i_iota(w.actA, cn, c0, st));
         PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h));
         PGPFA_TRY(pgpfa_i_logdet(w.L, n, cn, w.logdet, st));
         vi_dual_value_kernel<<<cn, 256, 0, st>>>(w.v, w.Kv, w.sums, w.logdet, w.actA, n, D, mean);
@@ -383,8 +353,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
     int sweeps = 0, not_converged = 0, total_factor = 0;
     for (int c0 = 0; c0 < R; c0 += chunk) {
         const int cn = (R - c0) < chunk ? (R - c0) : chunk;
-        iota2_kernel<<<(cn + 255) / 256, 256, 0, st>>>(w.actA, cn, c0);
-        PGPFA_LAUNCH_CHECK();
+        PGPFA_TRY(pgpfa_i_iota(w.actA, cn, c0, st));
         int *act = w.actA, *act_next = w.actB;
         int n_act = cn;
         for (int it = 0; it < max_iter && n_act > 0; it++) {
@@ -399,8 +368,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
             PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, n_act, st));
             PGPFA_TRY(pgpfa_i_timediag(w.ZT, act, vsm, n, q, T, n_act, st));
             VI_DISPATCH(vi_s_update_kernel, n_act, (size_t)N * q * sizeof(double), vsm, C, s, act, N, T, tol, w.conv, w.dsmax)
-            compact2_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, act_next, w.cnt);
-            PGPFA_LAUNCH_CHECK();
+            PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 1, act_next, w.cnt, st));
             PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
             PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
             n_act = h->pinned[0];
@@ -409,8 +377,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
         }
         not_converged += n_act;
         // ---- outputs at the fixed point
-        iota2_kernel<<<(cn + 255) / 256, 256, 0, st>>>(w.actA, cn, c0);
-        PGPFA_LAUNCH_CHECK();
+        PGPFA_TRY(pgpfa_i_iota(w.actA, cn, c0, st));
         VI_DISPATCH(vi_rates_kernel, cn, smem_cd(N, q), x, s, nullptr, y, C, d, w.actA, N, T, 0, lam, w.v, w.W, w.sums)
         PGPFA_TRY(pgpfa_i_prior_apply(K, w.v, w.Kv, w.actA, cn, q, T, st));
         PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h));

@@ -361,6 +361,20 @@ int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const doub
     return PGPFA_ERR_ARG;
 }
 
+int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st) {
+    if (n <= 0) return PGPFA_OK;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, start);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+// act_out <- the entries of act_in whose state (conv[trial]) has its bit set in keep_mask; *n_out = how many
+int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st) {
+    compact_active_kernel<<<1, 1024, 0, st>>>(act_in, n_in, conv, keep_mask, act_out, n_out);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st) {
     if (R <= 0) return PGPFA_OK;

@@ -72,3 +72,5 @@ int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const doub
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);
+int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st);
+int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st);
