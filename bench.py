@@ -181,7 +181,7 @@ def run_ours(args):
         liks.append(lik)
         newton_its.append(est.stats["max_newton_iters"]); facts += est.stats["factorizations"]
         cd_its.append(cd_it); tau_evals.append(nfev)
-        chord_its.append(est.stats["chord_iters"]); fallback.append(est.stats["fresh_chord_sweeps"])
+        chord_its.append(est.stats["pcg_newton_iters"]); fallback.append(est.stats["pcg_iters"])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -258,7 +258,7 @@ def run_ours(args):
                 "share_of_step": fac_ms / ms,
                 "other_ms_per_step": {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
                                       "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
-                                      "factor": fac_ms / args.steps},
+                                      "factor": fac_ms / args.steps, "block_jacobi_factor": prof_ms[5] / args.steps},
                 "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
                 "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
     cpu = None
@@ -282,7 +282,7 @@ def run_ours(args):
                     "api": "inference.laplace + learning.updateParams with host numpy inputs/outputs each step"},
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
-                       "tau_evals": tau_evals, "chord_iters_per_step": chord_its, "fresh_factor_sweeps_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
+                       "tau_evals": tau_evals, "inexact_newton_iters_per_step": chord_its, "pcg_iters_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:

@@ -78,12 +78,11 @@ class DeviceTrials:
         self.offset = int(offset)           # index of this shard's first trial in the full experiment
         self.R_total = int(R_total) if R_total is not None else int(self.reducer.sum_scalar(self.R))
         self._lap_ws = None
-        self._factor_key = None      # (R,q,T) when the Laplace workspace holds every trial's factor at its last mode
         self._cd_ws = None
         self._tau_ws = None
 
     # ------------------------------------------------------------------ E-step
-    def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, reuse_factor=True):
+    def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True):
         R, N, T = self.y.shape
         q = params.q
         if self._lap_ws is None or self._lap_ws[0] != (R, q, T):
@@ -92,14 +91,8 @@ class DeviceTrials:
             budget = int(free * 0.80) - R * q * T * T * 8      # leave room for vsmGP
             nbytes = full if full <= budget else max(budget, _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, 1))
             self._lap_ws = ((R, q, T), _lib.workspace(nbytes))
-            self._factor_key = None
-        # factors kept from the previous E-step of the SAME trials drive cheap chord iterations (warm start only)
-        reuse = reuse_factor and x0 is not None and self._factor_key == (R, q, T)
-        self._factor_key = None
         res = kn.laplace_solve(self.y, params.C, params.d, params.Kinv, x0=x0, tol=tol, max_newton=max_newton,
-                               want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], reuse_factor=reuse)
-        if res.rc == 0 and res.stats["factors_kept"]:
-            self._factor_key = (R, q, T)
+                               want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton)
         if int(res.info.abs().max()) != 0:
             raise FloatingPointError("posterior Hessian not positive definite for %d trial(s)"
                                      % int((res.info != 0).sum()))

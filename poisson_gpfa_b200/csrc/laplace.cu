@@ -6,6 +6,8 @@
 //   f      = sum lam - y h + 0.5 x^T Kinv x
 //   g[k,t] = sum_n C[n,k] (lam - y)[n,t] + (Kinv_k x_k)[t]
 //   W[k,l,t] = sum_n C[n,k] C[n,l] lam[n,t]        (H = blkdiag(Kinv) + scatter(W))
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <set>
 #include <utility>
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
     const double *__restrict__ d, const double *__restrict__ off, const int *act, int N, int T, double tol,
     double *__restrict__ fcur, int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen,
-    int chord_it, LooMap loo) {
+    int chord_it, LooMap loo, double *__restrict__ pcg_s) {
     extern __shared__ double sm[];
     double *Cs = sm;
     double *ds = sm + N * Q;
@@ -211,6 +213,14 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
             // already converged (late EM: parameters barely move): certified by the observed contraction
             if (chord_it >= 1 && sl < 0.5 * prev && sl * (sl / prev) / (1.0 - sl / prev) <= tol * scale) state = 1;
             if (chord_it == 0 && sl <= 0.01 * tol * scale) state = 1;
+        } else if (chord_it >= 2000) {
+            // inexact Newton (PCG to relative residual eta): error after this step ~ c sl^2 + 2 eta sl.
+            // The next solve is asked for eta' ~ 0.1 * (relative step just taken): superlinear overall.
+            const double eta = pcg_s[trial * 4 + 2];
+            const double rel = sl / scale;
+            state = (0.2 * rel * rel + 2.0 * eta * rel <= 0.1 * tol || rel <= 0.01 * tol) ? 1 : 0;
+            if (state == 0 && (alpha < 0.01 || chord_it >= 2000 + 14)) state = 2;   // struggling: hand over to exact Newton
+            pcg_s[trial * 4 + 2] = fmin(1e-2, fmax(1e-9, 0.03 * rel));
         } else {
             const double rho = (prev > 0.0) ? sl / prev : 1.0;
             state = 0;
@@ -268,6 +278,12 @@ __global__ void __launch_bounds__(256) polish_kernel(double *__restrict__ x, con
     if (threadIdx.x == 0) steplen[trial] = dmax;
 }
 
+// block-Jacobi system ids of a trial list: out[i*q + k] = act[i]*q + k
+__global__ void expand_slots_kernel(const int *act, int n, int q, int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * q) out[i] = act[i / q] * q + (i % q);
+}
+
 __global__ void scatter_slots_kernel(const int *act, int n, int *map) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) map[act[i]] = i;
@@ -299,6 +315,130 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
     *o = (accumulate ? *o : 0.0) + (a0 + a1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched preconditioned conjugate gradients for the Newton systems H(x) delta = -g, H v = Kinv v + W v
+// (per-bin q x q blocks), preconditioner = the factor kept from the previous E-step (FP32 mirror).
+// One CTA per trial; the per-trial scalars live in pcg_s[trial*4 + {rz, bnorm2, eta, unused}].
+// ---------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict__ g, double *__restrict__ r,
+                                                       double *__restrict__ delta, const int *act, int T, int first_outer,
+                                                       double *__restrict__ pcg_s, int *__restrict__ conv) {
+    __shared__ double red[32];
+    const int trial = act ? act[blockIdx.x] : blockIdx.x;
+    const size_t base = (size_t)trial * Q * T;
+    double bb = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
+        const double gv = g[base + i];
+        r[base + i] = -gv;
+        delta[base + i] = 0.0;
+        bb += gv * gv;
+    }
+    bb = block_sum(bb, red);
+    if (threadIdx.x == 0) {
+        pcg_s[trial * 4 + 0] = 0.0;
+        pcg_s[trial * 4 + 1] = bb;
+        if (first_outer) pcg_s[trial * 4 + 2] = 1e-2;
+        conv[trial] = (bb == 0.0) ? 1 : 0;
+    }
+}
+
+// p = z + beta p (beta = 0 on the first call), rz = r.z
+template <int Q>
+__global__ void __launch_bounds__(256) pcg_dir_kernel(const double *__restrict__ r, const double *__restrict__ z,
+                                                      double *__restrict__ p, const int *act, int T, int first,
+                                                      double *__restrict__ pcg_s) {
+    __shared__ double red[32];
+    const int trial = act ? act[blockIdx.x] : blockIdx.x;
+    const size_t base = (size_t)trial * Q * T;
+    double rz = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) rz += r[base + i] * z[base + i];
+    rz = block_sum(rz, red);
+    const double beta = first ? 0.0 : rz / pcg_s[trial * 4 + 0];
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) p[base + i] = z[base + i] + (first ? 0.0 : beta * p[base + i]);
+    __syncthreads();
+    if (threadIdx.x == 0) pcg_s[trial * 4 + 0] = rz;
+}
+
+// Hp = Kp + W p ; alpha = rz / p.Hp ; delta += alpha p ; r -= alpha Hp ; converged when |r| <= eta |b|
+template <int Q>
+__global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict__ p, const double *__restrict__ Kp,
+                                                       const double *__restrict__ W, double *__restrict__ Hp,
+                                                       double *__restrict__ delta, double *__restrict__ r,
+                                                       const int *act, int T, double *__restrict__ pcg_s,
+                                                       int *__restrict__ conv) {
+    __shared__ double red[32];
+    const int trial = act ? act[blockIdx.x] : blockIdx.x;
+    const size_t base = (size_t)trial * Q * T;
+    const double *Wt = W + (size_t)trial * Q * Q * T;
+    double pHp = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double pk[Q];
+#pragma unroll
+        for (int k = 0; k < Q; k++) pk[k] = p[base + (size_t)k * T + t];
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            double hv = Kp[base + (size_t)k * T + t];
+#pragma unroll
+            for (int l = 0; l < Q; l++) hv += Wt[(size_t)(k * Q + l) * T + t] * pk[l];
+            Hp[base + (size_t)k * T + t] = hv;
+            pHp += pk[k] * hv;
+        }
+    }
+    pHp = block_sum(pHp, red);
+    const double alpha = pcg_s[trial * 4 + 0] / pHp;
+    double rr = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
+        delta[base + i] += alpha * p[base + i];
+        const double rv = r[base + i] - alpha * Hp[base + i];
+        r[base + i] = rv;
+        rr += rv * rv;
+    }
+    rr = block_sum(rr, red);
+    if (threadIdx.x == 0) {
+        const double eta = pcg_s[trial * 4 + 2];
+        conv[trial] = (rr <= eta * eta * pcg_s[trial * 4 + 1] || !(pHp > 0.0)) ? 1 : 0;
+    }
+}
+
+template <int Q>
+int launch_pcg_init(const double *g, double *r, double *delta, const int *act, int nslots, int T, int first_outer,
+                    double *pcg_s, int *conv, cudaStream_t st) {
+    pcg_init_kernel<Q><<<nslots, 256, 0, st>>>(g, r, delta, act, T, first_outer, pcg_s, conv);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int Q>
+int launch_pcg_dir(const double *r, const double *z, double *p, const int *act, int nslots, int T, int first, double *pcg_s,
+                   cudaStream_t st) {
+    pcg_dir_kernel<Q><<<nslots, 256, 0, st>>>(r, z, p, act, T, first, pcg_s);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int Q>
+int launch_pcg_step(const double *p, const double *Kp, const double *W, double *Hp, double *delta, double *r, const int *act,
+                    int nslots, int T, double *pcg_s, int *conv, cudaStream_t st) {
+    pcg_step_kernel<Q><<<nslots, 256, 0, st>>>(p, Kp, W, Hp, delta, r, act, T, pcg_s, conv);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+#define PCG_DISPATCH(FN, ...)                                  \
+    switch (q) {                                               \
+        case 1: PGPFA_TRY(FN<1>(__VA_ARGS__)); break;          \
+        case 2: PGPFA_TRY(FN<2>(__VA_ARGS__)); break;          \
+        case 3: PGPFA_TRY(FN<3>(__VA_ARGS__)); break;          \
+        case 4: PGPFA_TRY(FN<4>(__VA_ARGS__)); break;          \
+        case 5: PGPFA_TRY(FN<5>(__VA_ARGS__)); break;          \
+        case 6: PGPFA_TRY(FN<6>(__VA_ARGS__)); break;          \
+        case 7: PGPFA_TRY(FN<7>(__VA_ARGS__)); break;          \
+        case 8: PGPFA_TRY(FN<8>(__VA_ARGS__)); break;          \
+        case 9: PGPFA_TRY(FN<9>(__VA_ARGS__)); break;          \
+        case 10: PGPFA_TRY(FN<10>(__VA_ARGS__)); break;        \
+        case 11: PGPFA_TRY(FN<11>(__VA_ARGS__)); break;        \
+        case 12: PGPFA_TRY(FN<12>(__VA_ARGS__)); break;        \
+        default: return PGPFA_ERR_ARG;                         \
+    }
+
 template <int Q>
 int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const double *off,
                 const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st, LooMap loo) {
@@ -313,11 +453,12 @@ int launch_eval(const double *x, const double *Kx, const double *y, const double
 template <int Q>
 int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
                       const double *C, const double *d, const double *off, const int *act, int nslots, int N, int T, double tol,
-                      double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st, LooMap loo) {
+                      double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st, LooMap loo,
+                      double *pcg_s) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it, loo);
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it, loo, pcg_s);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -351,10 +492,10 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st, const double *off, LooMap loo) {
+                       cudaStream_t st, const double *off, LooMap loo, double *pcg_s) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st, loo);
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st, loo, pcg_s);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -406,8 +547,10 @@ std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct LapWs {
-    double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen;
-    int *conv, *actA, *actB, *actC, *lslot, *cnt;
+    double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen, *pr, *pz, *pp, *pHp, *pcg_s;
+    int *conv, *actA, *actB, *actC, *lslot, *cnt, *xact;
+    double *LB, *DB;          // block-Jacobi factors: (trial*q + k) x lt(T) tiles, (trial*q+k) x nb(T) tiles
+    float *LB32, *DB32;
     int2 *pairs;
     double *L, *Dinv, *ZT;
     float *L32, *D32;
@@ -418,16 +561,21 @@ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     const size_t n = (size_t)q * T;
     size_t b = 0;
-    b += 4 * align_up((size_t)R * n * 8);
+    b += 8 * align_up((size_t)R * n * 8) + align_up((size_t)R * 32);
     b += align_up((size_t)R * q * q * T * 8);
     b += 2 * align_up((size_t)R * 8);
-    b += 5 * align_up((size_t)R * 4) + 256;
+    b += 5 * align_up((size_t)R * 4) + 256 + align_up((size_t)R * q * 4);
     b += align_up((size_t)npairs_max * sizeof(int2));
     return b;
 }
+size_t lap_block_bytes(int q, int T) {      // block-Jacobi preconditioner factors of one trial (FP64 + FP32 mirrors)
+    const int nbT = pgpfa_nb(T);
+    return (size_t)q * (pgpfa_ltiles(nbT) + nbT) * PGPFA_TILE * 12;
+}
 size_t lap_per_trial_bytes(int q, int T) {
     const int nb = pgpfa_nb(q * T);
-    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8 + (size_t)(pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 4;
+    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8 + (size_t)(pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 4 +
+           lap_block_bytes(q, T);
 }
 }  // namespace
 
@@ -440,7 +588,7 @@ extern "C" long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chun
 
 static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C, const double *d,
                               const double *Kinv, double *x, int R, int q, int N, int T, double tol,
-                              int max_newton, int reuse_factor, double *f_out, double *vsm, double *vsmGP,
+                              int max_newton, int flags, double *f_out, double *vsm, double *vsmGP,
                               double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
                               int *stats_out, cudaStream_t st, LooMap loo, bool posterior_pass) {
     if (!h || !y || !C || !d || !Kinv || !x || !f_out || !niter || !info || !workspace) return PGPFA_ERR_ARG;
@@ -452,7 +600,6 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     if ((size_t)ws_bytes < fixed + per) return PGPFA_ERR_WORKSPACE;
     long long chunk_ll = ((size_t)ws_bytes - fixed) / per;
     const int chunk = (int)(chunk_ll > R ? R : chunk_ll);
-    if (chunk < R) reuse_factor = 0;     // kept factors are only valid when all trials share one chunk
 
     unsigned char *p = static_cast<unsigned char *>(workspace);
     p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(p)));
@@ -460,6 +607,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     auto take = [&](size_t bytes) { unsigned char *r = p; p += align_up(bytes); return r; };
     const size_t vec = (size_t)R * n * 8;
     w.Kx = (double *)take(vec); w.Kd = (double *)take(vec); w.g = (double *)take(vec); w.dx = (double *)take(vec);
+    w.pr = (double *)take(vec); w.pz = (double *)take(vec); w.pp = (double *)take(vec); w.pHp = (double *)take(vec);
+    w.pcg_s = (double *)take((size_t)R * 32);
     w.W = (double *)take((size_t)R * q * q * T * 8);
     w.fcur = (double *)take((size_t)R * 8); w.steplen = (double *)take((size_t)R * 8);
     w.conv = (int *)take((size_t)R * 4); w.actA = (int *)take((size_t)R * 4); w.actB = (int *)take((size_t)R * 4);
@@ -471,6 +620,13 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.ZT = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
     w.L32 = (float *)take((size_t)chunk * ltl * PGPFA_TILE * 4);
     w.D32 = (float *)take((size_t)chunk * nb * PGPFA_TILE * 4);
+    const int nbT = pgpfa_nb(T);
+    const long long ltT = pgpfa_ltiles(nbT);
+    w.LB = (double *)take((size_t)chunk * q * ltT * PGPFA_TILE * 8);
+    w.DB = (double *)take((size_t)chunk * q * nbT * PGPFA_TILE * 8);
+    w.LB32 = (float *)take((size_t)chunk * q * ltT * PGPFA_TILE * 4);
+    w.DB32 = (float *)take((size_t)chunk * q * nbT * PGPFA_TILE * 4);
+    w.xact = (int *)take((size_t)R * q * 4);
 
     PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
@@ -481,7 +637,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
 
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
-    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, chord_its = 0, chord_fallback = 0, fresh_sweeps = 0;
+    const bool dbg = getenv("PGPFA_DEBUG") != nullptr;
+    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, chord_its = 0, chord_fallback = 0, fresh_sweeps = 0, pcg_its = 0;
     const double solve_bytes = 2.0 * (double)(ltl + nb) * PGPFA_TILE * 8;
     auto read_count = [&](int &dst) -> int {
         PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -496,33 +653,69 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         PGPFA_LAUNCH_CHECK();
         int *act = w.actA, *act_next = w.actB;
         int n_act = cn;
-        // ---- phase A: a few chord iterations with the factor kept from the previous E-step (same trials, nearby
-        // parameters): x <- x - (L L^T)_old^-1 g(x).  Linear convergence (contraction ~0.4 while tau still
-        // moves ~10% per EM iteration), 4.5 ms per sweep against 64 ms per factorisation: they replace the
-        // first (far-from-quadratic) Newton iteration.
-        if (reuse_factor) {
-            const double tol_chord = tol;
-            for (int it = 0; it < 6 && n_act > 0; it++) {
+        // ---- phase A: inexact Newton.  The Newton systems H(x_k) delta = -g are solved by conjugate gradients with a
+        // block-Jacobi preconditioner M = blkdiag_k(Kinv_k + diag(W_kk)) (drops the cross-latent coupling of W):
+        // cond(M^-1 H) ~ 5, one q-fold batch of T x T tiled Cholesky factorisations per Newton iteration (1/q^2 of
+        // the flops of the full factorisation), and per CG iteration one fused H v product plus one pair of small
+        // triangular solves streaming the FP32 mirrors.  No qT x qT factorisation before the one at the mode.
+        if (flags & 1) {
+            PgpfaMatSrc mb;
+            mb.Kinv = Kinv; mb.W = w.W; mb.dense = nullptr; mb.q = 1; mb.T = T; mb.n = T; mb.diag_scale = 1.0; mb.blk_q = q; mb.blk_base = c0 * q;
+            const double blk_solve_bytes = 2.0 * (double)q * (double)(ltT + nbT) * PGPFA_TILE * 4;
+            for (int it = 0; it < 16 && n_act > 0; it++) {
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
                 PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
+                PCG_DISPATCH(launch_pcg_init, w.g, w.pr, w.dx, act, n_act, T, it == 0, w.pcg_s, w.conv, st)
                 pgpfa_prof_end(h, st);
-                pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
-                PGPFA_TRY(pgpfa_i_solve32(w.L32, w.D32, w.g, w.dx, -1.0, act, n, n_act, st, c0));
-                pgpfa_prof_end(h, st);
-                h->prof_work[PGPFA_PROF_SOLVE] += (double)n_act * solve_bytes * 0.5;
+                // preconditioner factors of this Newton iteration (ids trial*q + k, stored by id)
+                // (factored once per E-step: W_kk moves little between Newton iterations and any SPD preconditioner
+                // leaves the CG solution unchanged)
+                if (it == 0) {
+                    pgpfa_prof_begin(h, PGPFA_PROF_BLOCKFACTOR, st);
+                    expand_slots_kernel<<<(n_act * q + 255) / 256, 256, 0, st>>>(act, n_act, q, w.xact);
+                    PGPFA_LAUNCH_CHECK();
+                    PGPFA_TRY(pgpfa_i_factor(mb, w.LB, w.DB, nullptr, w.xact, nullptr, n_act * q, st, h, w.LB32, w.DB32));
+                    pgpfa_prof_end(h, st);
+                }
+                // PCG over the trials of this Newton iteration; converged trials drop out of `cg`
+                int *cg = act_next, *cg_next = w.actC;
+                PGPFA_CUDA_TRY(cudaMemcpyAsync(cg, act, (size_t)n_act * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                int n_cg = n_act;
+                for (int ci = 0; ci < 60 && n_cg > 0; ci++) {
+                    pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
+                    expand_slots_kernel<<<(n_cg * q + 255) / 256, 256, 0, st>>>(cg, n_cg, q, w.xact);
+                    PGPFA_LAUNCH_CHECK();
+                    PGPFA_TRY(pgpfa_i_solve32(w.LB32, w.DB32, w.pr, w.pz, 1.0, w.xact, T, n_cg * q, st, c0 * q));
+                    pgpfa_prof_end(h, st);
+                    h->prof_work[PGPFA_PROF_SOLVE] += (double)n_cg * blk_solve_bytes;
+                    pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
+                    PCG_DISPATCH(launch_pcg_dir, w.pr, w.pz, w.pp, cg, n_cg, T, ci == 0, w.pcg_s, st)
+                    PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.pp, w.Kd, cg, n_cg, q, T, st));
+                    PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, n_cg, T, w.pcg_s, w.conv, st)
+                    pgpfa_prof_end(h, st);
+                    compact_active_kernel<<<1, 1024, 0, st>>>(cg, n_cg, w.conv, 1, cg_next, w.cnt);
+                    PGPFA_LAUNCH_CHECK();
+                    PGPFA_TRY(read_count(n_cg));
+                    int *t3 = cg; cg = cg_next; cg_next = t3;
+                    pcg_its++;
+                    if (dbg) fprintf(stderr, "[pgpfa] outer %d cg %d: %d trials still iterating\n", it, ci, n_cg);
+                }
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
-                PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol_chord, w.fcur,
-                                             w.conv, niter, w.steplen, it, st, nullptr, loo));
+                PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
+                                             niter, w.steplen, 2000 + it, st, nullptr, loo, w.pcg_s));
                 pgpfa_prof_end(h, st);
-                compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, act_next, w.cnt);
+                int *outp = (act == w.actA) ? w.actB : w.actA;
+                compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, outp, w.cnt);
                 PGPFA_LAUNCH_CHECK();
                 PGPFA_TRY(read_count(n_act));
-                int *tmp = act; act = act_next; act_next = tmp;
+                if (dbg) fprintf(stderr, "[pgpfa] outer %d done: %d trials continue\n", it, n_act);
+                act = outp;
+                act_next = (act == w.actA) ? w.actB : w.actA;
                 chord_its = it + 1;
             }
-            // trials that stalled (state 2) or ran out of chord iterations (state 0) go to exact Newton
+            // trials that struggled (state 2) or ran out of inexact-Newton iterations (state 0) go to exact Newton
             iota_kernel<<<(cn + 255) / 256, 256, 0, st>>>(act_next, cn, c0);
             PGPFA_LAUNCH_CHECK();
             compact_active_kernel<<<1, 1024, 0, st>>>(act_next, cn, w.conv, 5, act, w.cnt);
@@ -630,19 +823,19 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         stats_out[4] = chord_its;
         stats_out[5] = chord_fallback;
         stats_out[6] = (chunk >= R) ? 1 : 0;     // the workspace now holds every trial's factor at its mode
-        stats_out[7] = fresh_sweeps;
+        stats_out[7] = fresh_sweeps + 1000 * pcg_its;
     }
     return not_converged ? PGPFA_ERR_NOT_CONVERGED : PGPFA_OK;
 }
 
 extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d,
                                    const double *Kinv, double *x, int R, int q, int N, int T, double tol,
-                                   int max_newton, int reuse_factor, double *f_out, double *vsm, double *vsmGP,
+                                   int max_newton, int flags, double *f_out, double *vsm, double *vsmGP,
                                    double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
                                    int *stats_out, cudaStream_t st) {
     LooMap loo;
     loo.ymap = nullptr; loo.excl = nullptr;
-    return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, reuse_factor, f_out, vsm, vsmGP, cov_dense,
+    return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, flags, f_out, vsm, vsmGP, cov_dense,
                               niter, info, workspace, ws_bytes, stats_out, st, loo, true);
 }
 
@@ -678,7 +871,7 @@ extern "C" int pgpfa_loo_predict(pgpfa_handle_t h, const double *y, const double
     LooMap loo;
     loo.ymap = ymap; loo.excl = excl;
     // f_out scratch: the first P doubles of the workspace tail are not needed afterwards -> use err as f_out
-    int rc = laplace_solve_impl(h, y, C, d, Kinv, x, P, q, N, T, tol, max_newton, 0, err, nullptr, nullptr, nullptr, niter, info,
+    int rc = laplace_solve_impl(h, y, C, d, Kinv, x, P, q, N, T, tol, max_newton, 1, err, nullptr, nullptr, nullptr, niter, info,
                                 workspace, ws_bytes, stats_out, st, loo, false);
     if (rc != PGPFA_OK && rc != PGPFA_ERR_NOT_CONVERGED) return rc;
     switch (q) {

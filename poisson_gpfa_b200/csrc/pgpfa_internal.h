@@ -12,6 +12,8 @@ struct PgpfaMatSrc {
     const double *dense;  // (slots, n, n)
     int q, T, n;
     double diag_scale;
+    int blk_q = 0;        // > 0: block-Jacobi systems M = Kinv_k + diag(W_kk), id = trial*blk_q + k, n = T, q = 1
+    int blk_base = 0;     // block-Jacobi factors are stored at (id - blk_base)
 };
 
 struct pgpfa_handle_s;
@@ -39,6 +41,7 @@ enum {
     PGPFA_PROF_EVAL = 2,      // prior mat-vec + fused rates/gradient/W + line search
     PGPFA_PROF_TRTRI = 3,     // triangular inverse; work = trials * n^3/3 flops
     PGPFA_PROF_SLICES = 4,    // time-diagonals + selected inverse tiles
+    PGPFA_PROF_BLOCKFACTOR = 5,  // block-Jacobi preconditioner factorisations (q T x T systems per trial)
     PGPFA_PROF_SLOTS = 8
 };
 struct PgpfaProfSpan { cudaEvent_t e0, e1; int slot; };
@@ -68,7 +71,7 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
-                       cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo());
+                       cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo(), double *pcg_s = nullptr);
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);

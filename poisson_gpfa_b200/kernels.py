@@ -179,7 +179,7 @@ class LaplaceResult:
 
 
 def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True, want_vsmGP=True, want_cov=False,
-                  max_ws_bytes=None, ws=None, reuse_factor=False):
+                  max_ws_bytes=None, ws=None, inexact_newton=True):
     """Batched Newton E-step (pgpfa_laplace_solve). y (R,N,T); returns LaplaceResult with device tensors."""
     R, N, T = y.shape
     q = C.shape[1]
@@ -203,12 +203,12 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
         ws = workspace(nbytes)
     stats = (ctypes.c_int * 8)()
     res.rc = call("pgpfa_laplace_solve", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(x), R, q, N, T, float(tol),
-                  int(max_newton), int(bool(reuse_factor)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov), ptr(res.niter),
+                  int(max_newton), int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov), ptr(res.niter),
                   ptr(res.info), ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(),
                   allow=(_lib.ERR_NOT_CONVERGED,))
     res.stats = {"factorizations": stats[0], "max_newton_iters": stats[1], "not_converged": stats[2],
-                 "chunk": stats[3], "chord_iters": stats[4], "chord_fallback_trials": stats[5],
-                 "factors_kept": bool(stats[6]), "fresh_chord_sweeps": stats[7]}
+                 "chunk": stats[3], "pcg_newton_iters": stats[4], "fallback_trials": stats[5],
+                 "fresh_chord_sweeps": stats[7] % 1000, "pcg_iters": stats[7] // 1000}
     return res
 
 

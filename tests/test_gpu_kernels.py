@@ -220,32 +220,29 @@ def test_pautosum_and_tau_eval(q, T, R):
     assert rel(grad2, g2) <= 1e-8
 
 
-def test_estep_factor_reuse_reaches_same_fixed_point():
-    """Chord iterations with the factors kept from the previous E-step (nearby parameters) must land on the
-    same posterior as a fresh exact-Newton solve, with fewer factorisations."""
+def test_inexact_newton_pcg_reaches_same_fixed_point():
+    """The inexact-Newton path (conjugate gradients with the block-Jacobi preconditioner, no qT x qT factorisation
+    before the mode) and the exact-Newton path (fresh factorisation per iteration) must land on the same posterior."""
     from poisson_gpfa_b200 import core
     q, N, T, R = 4, 30, 100, 6
     ex, ys, params = problem(77, q, N, T, R)
     trials = core.DeviceTrials(dev(np.stack(ys)), 10)
     pA = core.DeviceParams(params['C'], params['d'], params['tau'], T, 10)
-    estA = trials.estep_laplace(pA)
-    assert estA.stats["chord_iters"] == 0
-    rng = np.random.RandomState(0)
-    pB_np = {'C': params['C'] + 0.01 * rng.randn(N, q), 'd': params['d'] + 0.01 * rng.randn(N), 'tau': params['tau'] * 1.01}
-    pB = core.DeviceParams(pB_np['C'], pB_np['d'], pB_np['tau'], T, 10)
-    estB = trials.estep_laplace(pB, x0=estA.x)
-    assert estB.stats["chord_iters"] >= 1
-    fresh = core.DeviceTrials(dev(np.stack(ys)), 10).estep_laplace(pB, x0=estA.x.clone(), reuse_factor=False)
-    assert estB.stats["factorizations"] <= fresh.stats["factorizations"]
-    ir, lik, _, _ = po.laplace_struct(ys, pB_np, T, 10, want_cov=False)
-    for est in (estB, fresh):
+    ir, lik, _, _ = po.laplace_struct(ys, params, T, 10, want_cov=False)
+    cold_pcg = trials.estep_laplace(pA)
+    cold_newton = trials.estep_laplace(pA, inexact_newton=False)
+    assert cold_pcg.stats["pcg_iters"] > 0 and cold_pcg.stats["factorizations"] == R       # only the one at the mode
+    assert cold_newton.stats["pcg_iters"] == 0 and cold_newton.stats["factorizations"] > R
+    for est in (cold_pcg, cold_newton):
         assert rel(est.x, np.stack(ir['post_mean'])) <= 1e-8
         assert rel(est.vsm, np.stack(ir['post_vsm'])) <= 1e-8
         assert rel(est.vsmGP, np.stack([v.transpose(2, 0, 1) for v in ir['post_vsmGP']])) <= 1e-8
-    # far-away parameters: the chord iteration stalls and the trial falls back to exact Newton
-    pC_np = {'C': 2.0 * params['C'], 'd': params['d'] + 1.0, 'tau': params['tau'] * 3.0}
-    pC = core.DeviceParams(pC_np['C'], pC_np['d'], pC_np['tau'], T, 10)
-    estC = trials.estep_laplace(pC, x0=estB.x)
-    irC, _, _, _ = po.laplace_struct(ys, pC_np, T, 10, want_cov=False)
-    assert rel(estC.x, np.stack(irC['post_mean'])) <= 1e-8
-    assert rel(estC.vsm, np.stack(irC['post_vsm'])) <= 1e-8
+    # warm start under nearby and under far-away parameters
+    rng = np.random.RandomState(0)
+    for scale_C, shift_d, scale_tau in ((1.0, 0.0, 1.01), (2.0, 1.0, 3.0)):
+        pB_np = {'C': scale_C * params['C'] + 0.01 * rng.randn(N, q), 'd': params['d'] + shift_d, 'tau': params['tau'] * scale_tau}
+        pB = core.DeviceParams(pB_np['C'], pB_np['d'], pB_np['tau'], T, 10)
+        estB = trials.estep_laplace(pB, x0=cold_pcg.x)
+        irB, _, _, _ = po.laplace_struct(ys, pB_np, T, 10, want_cov=False)
+        assert rel(estB.x, np.stack(irB['post_mean'])) <= 1e-8
+        assert rel(estB.vsm, np.stack(irB['post_vsm'])) <= 1e-8

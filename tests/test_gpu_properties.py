@@ -127,7 +127,7 @@ def test_full_shape_properties():
         kn.mstep_cd_stats(trials.y[40:].contiguous(), est.x[40:].contiguous(), est.vsm[40:].contiguous(), th)
     assert rel(s_sum, s_all) <= 1e-12
     # (5) determinism: the same call twice gives identical bits
-    est4 = trials.estep_laplace(p, reuse_factor=False)
+    est4 = trials.estep_laplace(p)
     assert torch.equal(est4.x, est.x) and torch.equal(est4.vsmGP, est.vsmGP)
 
 

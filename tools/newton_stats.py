@@ -14,7 +14,7 @@ params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
 x0 = None
 hist = []
 for it in range(int(os.environ.get("ITERS", "6"))):
-    est = trials.estep_laplace(params, x0=x0, reuse_factor=False)
+    est = trials.estep_laplace(params, x0=x0, inexact_newton=False)
     C, d, cost, cd_it, _ = trials.mstep_cd(params, est)
     tau, det = trials.mstep_tau(params, trials.pautosum(est))
     newp = core.DeviceParams(C, d, tau, T, w["binSize"])

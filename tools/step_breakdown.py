@@ -25,5 +25,5 @@ for it in range(8):
     t4 = tick(); params = core.DeviceParams(C, d, tau, T, w["binSize"]); _ = params.Kinv
     t5 = tick(); x0 = est.x
     rows.append(dict(it=it, estep=(t1-t0)*1e3, cd=(t2-t1)*1e3, pauto=(t3-t2)*1e3, tau=(t4-t3)*1e3, kinv=(t5-t4)*1e3,
-                     cd_it=cd_it, nfev=det['nfev'], newton=est.stats['max_newton_iters'], chord=est.stats['chord_iters']))
+                     cd_it=cd_it, nfev=det['nfev'], newton=est.stats['max_newton_iters'], chord=est.stats['pcg_iters']))
 print(json.dumps(rows[3:], indent=0))
