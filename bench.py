@@ -258,7 +258,7 @@ def run_ours(args):
                 "share_of_step": fac_ms / ms,
                 "other_ms_per_step": {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
                                       "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
-                                      "factor": fac_ms / args.steps, "block_jacobi_factor": prof_ms[5] / args.steps},
+                                      "factor": fac_ms / args.steps, "cg_preconditioner_setup": prof_ms[5] / args.steps},
                 "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
                 "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
     cpu = None

@@ -29,7 +29,6 @@ struct MatSource {
     const double *dense;  // (slots, n, n) when Kinv == nullptr
     int q, T, n;
     double diag_scale;    // 1 (Laplace) or 1+1e-6 (variational, funs/inference.py:190)
-    int blk_q;            // > 0: block-Jacobi systems, id = trial*blk_q + k -> M = Kinv_k + diag(W_kk) (n = T, q = 1)
 };
 
 struct FragIdx {
@@ -66,15 +65,9 @@ __device__ __forceinline__ double mat_elem(const MatSource &src, int trial, int 
     } else {
         v = 0.0;
         const int s = f.rs[i], t = f.ct[j][e];
-        if (src.blk_q > 0) {
-            const int tr = trial / src.blk_q, k = trial - tr * src.blk_q;
-            v = __ldg(&src.Kinv[((size_t)k * src.T + s) * src.T + t]);
-            if (s == t) v += src.W[((size_t)tr * src.blk_q * src.blk_q + k * src.blk_q + k) * src.T + t];
-        } else {
-            const int k = f.rk[i], l = f.cl[j][e];
-            if (k == l) v = __ldg(&src.Kinv[((size_t)k * src.T + s) * src.T + t]);
-            if (s == t) v += src.W[((size_t)trial * src.q * src.q + k * src.q + l) * src.T + t];
-        }
+        const int k = f.rk[i], l = f.cl[j][e];
+        if (k == l) v = __ldg(&src.Kinv[((size_t)k * src.T + s) * src.T + t]);
+        if (s == t) v += src.W[((size_t)trial * src.q * src.q + k * src.q + l) * src.T + t];
     }
     if (r == c) v *= src.diag_scale;
     return v;
@@ -93,8 +86,6 @@ struct FactorArgs {
     int mode;           // panel kernel: 0 = Cholesky panel, 1 = triangular-inverse row
     int nslots, ntiles; // panel kernel, mode 0: 1-D grid decode (ntiles tile rows per slot)
     int fuse;           // panel kernel, mode 0: first-tile CTAs also factor diagonal tile step+1
-    int by_trial;       // factor storage is indexed by (id - store_base), id = act[slot], instead of the list position
-    int store_base;
 };
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
@@ -279,7 +270,7 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) ch
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lpos = blockIdx.x;
     const int trial = a.act ? a.act[lpos] : lpos;
-    const int slot = a.by_trial ? trial - a.store_base : lpos;
+    const int slot = lpos;
     const int j = a.step;
     const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
     double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
@@ -312,7 +303,6 @@ __global__ void __launch_bounds__(PGPFA_GEMM_THREADS, PGPFA_GEMM_CTAS_PER_SM) ch
         tile = blockIdx.x;
     }
     const int trial = a.act ? a.act[slot] : slot;
-    if (a.by_trial) slot = trial - a.store_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const long long ltl = (long long)a.nb * (a.nb + 1) / 2;
     double *Ls = a.L + (size_t)slot * ltl * PGPFA_TILE;
@@ -597,9 +587,7 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
     a.src.Kinv = ms.Kinv; a.src.W = ms.W; a.src.dense = ms.dense;
-    a.src.q = ms.q; a.src.T = ms.T; a.src.n = ms.n; a.src.diag_scale = ms.diag_scale; a.src.blk_q = ms.blk_q;
-    a.by_trial = ms.blk_q > 0 ? 1 : 0;
-    a.store_base = ms.blk_base;
+    a.src.q = ms.q; a.src.T = ms.T; a.src.n = ms.n; a.src.diag_scale = ms.diag_scale;
     a.L = L; a.Dinv = Dinv; a.ZT = ZT; a.act = act; a.info = info;
     a.L32 = L32; a.D32 = D32;
     a.nb = pgpfa_nb(ms.n);
@@ -627,7 +615,6 @@ int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int ns
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
     a.src.Kinv = nullptr; a.src.W = nullptr; a.src.dense = nullptr; a.src.q = 1; a.src.T = n; a.src.n = n; a.src.diag_scale = 1.0;
-    a.src.blk_q = 0; a.by_trial = 0; a.store_base = 0;
     a.L = const_cast<double *>(L); a.Dinv = const_cast<double *>(Dinv); a.ZT = ZT; a.act = nullptr; a.info = nullptr;
     a.L32 = nullptr; a.D32 = nullptr;
     a.nb = pgpfa_nb(n);

@@ -278,10 +278,28 @@ __global__ void __launch_bounds__(256) polish_kernel(double *__restrict__ x, con
     if (threadIdx.x == 0) steplen[trial] = dmax;
 }
 
-// block-Jacobi system ids of a trial list: out[i*q + k] = act[i]*q + k
-__global__ void expand_slots_kernel(const int *act, int n, int q, int *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n * q) out[i] = act[i / q] * q + (i % q);
+// wbar[k] = mean over the listed trials and all bins of W[trial][k,k][t]
+__global__ void __launch_bounds__(256) wdiag_mean_kernel(const double *__restrict__ W, const int *act, int n_act, int q, int T,
+                                                         double *__restrict__ wbar) {
+    __shared__ double red[32];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    const long long tot = (long long)n_act * T;
+    for (long long i = threadIdx.x; i < tot; i += blockDim.x) {
+        const int trial = act[i / T];
+        s += W[((size_t)trial * q * q + k * q + k) * T + (i % T)];
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) wbar[k] = s / (double)tot;
+}
+
+// M[k] = Kinv[k] + wbar[k] I
+__global__ void shift_diag_kernel(const double *__restrict__ Kinv, const double *__restrict__ wbar, int T, double *__restrict__ M) {
+    const int k = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int i = e / T, j = e - i * T;
+    M[(size_t)k * T * T + e] = Kinv[(size_t)k * T * T + e] + (i == j ? wbar[k] : 0.0);
 }
 
 __global__ void scatter_slots_kernel(const int *act, int n, int *map) {
@@ -548,9 +566,10 @@ std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all) {
 namespace {
 struct LapWs {
     double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen, *pr, *pz, *pp, *pHp, *pcg_s;
-    int *conv, *actA, *actB, *actC, *lslot, *cnt, *xact;
-    double *LB, *DB;          // block-Jacobi factors: (trial*q + k) x lt(T) tiles, (trial*q+k) x nb(T) tiles
-    float *LB32, *DB32;
+    int *conv, *actA, *actB, *actC, *lslot, *cnt, *pinfo;
+    double *Mk, *Minv, *wbar, *plogdet;     // shared CG preconditioner: (Kinv_k + wbar_k I)^-1, one T x T matrix per latent
+    void *pws;
+    long long pws_bytes;
     int2 *pairs;
     double *L, *Dinv, *ZT;
     float *L32, *D32;
@@ -564,18 +583,14 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += 8 * align_up((size_t)R * n * 8) + align_up((size_t)R * 32);
     b += align_up((size_t)R * q * q * T * 8);
     b += 2 * align_up((size_t)R * 8);
-    b += 5 * align_up((size_t)R * 4) + 256 + align_up((size_t)R * q * 4);
+    b += 5 * align_up((size_t)R * 4) + 256;
+    b += 2 * align_up((size_t)q * T * T * 8) + 3 * align_up((size_t)q * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
     b += align_up((size_t)npairs_max * sizeof(int2));
     return b;
 }
-size_t lap_block_bytes(int q, int T) {      // block-Jacobi preconditioner factors of one trial (FP64 + FP32 mirrors)
-    const int nbT = pgpfa_nb(T);
-    return (size_t)q * (pgpfa_ltiles(nbT) + nbT) * PGPFA_TILE * 12;
-}
 size_t lap_per_trial_bytes(int q, int T) {
     const int nb = pgpfa_nb(q * T);
-    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8 + (size_t)(pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 4 +
-           lap_block_bytes(q, T);
+    return (size_t)(2 * pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 8 + (size_t)(pgpfa_ltiles(nb) + nb) * PGPFA_TILE * 4;
 }
 }  // namespace
 
@@ -615,18 +630,16 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.actC = (int *)take((size_t)R * 4); w.lslot = (int *)take((size_t)R * 4);
     w.cnt = (int *)take(256);
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
+    w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)q * T * T * 8);
+    w.wbar = (double *)take((size_t)q * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
+    w.pws_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
+    w.pws = take((size_t)w.pws_bytes);
     w.L = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
     w.Dinv = (double *)take((size_t)chunk * nb * PGPFA_TILE * 8);
     w.ZT = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
     w.L32 = (float *)take((size_t)chunk * ltl * PGPFA_TILE * 4);
     w.D32 = (float *)take((size_t)chunk * nb * PGPFA_TILE * 4);
-    const int nbT = pgpfa_nb(T);
-    const long long ltT = pgpfa_ltiles(nbT);
-    w.LB = (double *)take((size_t)chunk * q * ltT * PGPFA_TILE * 8);
-    w.DB = (double *)take((size_t)chunk * q * nbT * PGPFA_TILE * 8);
-    w.LB32 = (float *)take((size_t)chunk * q * ltT * PGPFA_TILE * 4);
-    w.DB32 = (float *)take((size_t)chunk * q * nbT * PGPFA_TILE * 4);
-    w.xact = (int *)take((size_t)R * q * 4);
+
 
     PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
@@ -653,29 +666,27 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         PGPFA_LAUNCH_CHECK();
         int *act = w.actA, *act_next = w.actB;
         int n_act = cn;
-        // ---- phase A: inexact Newton.  The Newton systems H(x_k) delta = -g are solved by conjugate gradients with a
-        // block-Jacobi preconditioner M = blkdiag_k(Kinv_k + diag(W_kk)) (drops the cross-latent coupling of W):
-        // cond(M^-1 H) ~ 5, one q-fold batch of T x T tiled Cholesky factorisations per Newton iteration (1/q^2 of
-        // the flops of the full factorisation), and per CG iteration one fused H v product plus one pair of small
-        // triangular solves streaming the FP32 mirrors.  No qT x qT factorisation before the one at the mode.
+        // ---- phase A: inexact Newton.  The Newton systems H(x_k) delta = -g are solved by conjugate gradients.
+        // Preconditioner: M_k = Kinv_k + wbar_k I per latent (the bin- and trial-dependent diagonal W_kk replaced by
+        // its mean, the cross-latent coupling dropped), ONE T x T matrix per latent shared by all trials: inverted
+        // once per E-step (q small SPD inverses) and applied with the same batched mat-vec kernel as the prior.
+        // cond(M^-1 H) ~ 6-10, so a Newton solve to 1e-5 takes ~15 CG iterations, each one fused H v product and
+        // two batched T x T mat-vecs: no qT x qT factorisation before the one at the mode.
         if (flags & 1) {
-            PgpfaMatSrc mb;
-            mb.Kinv = Kinv; mb.W = w.W; mb.dense = nullptr; mb.q = 1; mb.T = T; mb.n = T; mb.diag_scale = 1.0; mb.blk_q = q; mb.blk_base = c0 * q;
-            const double blk_solve_bytes = 2.0 * (double)q * (double)(ltT + nbT) * PGPFA_TILE * 4;
             for (int it = 0; it < 16 && n_act > 0; it++) {
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
                 PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
                 PCG_DISPATCH(launch_pcg_init, w.g, w.pr, w.dx, act, n_act, T, it == 0, w.pcg_s, w.conv, st)
                 pgpfa_prof_end(h, st);
-                // preconditioner factors of this Newton iteration (ids trial*q + k, stored by id)
-                // (factored once per E-step: W_kk moves little between Newton iterations and any SPD preconditioner
-                // leaves the CG solution unchanged)
                 if (it == 0) {
                     pgpfa_prof_begin(h, PGPFA_PROF_BLOCKFACTOR, st);
-                    expand_slots_kernel<<<(n_act * q + 255) / 256, 256, 0, st>>>(act, n_act, q, w.xact);
+                    wdiag_mean_kernel<<<q, 256, 0, st>>>(w.W, act, n_act, q, T, w.wbar);
                     PGPFA_LAUNCH_CHECK();
-                    PGPFA_TRY(pgpfa_i_factor(mb, w.LB, w.DB, nullptr, w.xact, nullptr, n_act * q, st, h, w.LB32, w.DB32));
+                    dim3 gsh((T * T + 255) / 256, q);
+                    shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, T, w.Mk);
+                    PGPFA_LAUNCH_CHECK();
+                    PGPFA_TRY(pgpfa_spd_inverse_batched(w.Mk, q, T, w.Minv, w.plogdet, w.pinfo, w.pws, w.pws_bytes, st));
                     pgpfa_prof_end(h, st);
                 }
                 // PCG over the trials of this Newton iteration; converged trials drop out of `cg`
@@ -683,13 +694,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                 PGPFA_CUDA_TRY(cudaMemcpyAsync(cg, act, (size_t)n_act * sizeof(int), cudaMemcpyDeviceToDevice, st));
                 int n_cg = n_act;
                 for (int ci = 0; ci < 60 && n_cg > 0; ci++) {
-                    pgpfa_prof_begin(h, PGPFA_PROF_SOLVE, st);
-                    expand_slots_kernel<<<(n_cg * q + 255) / 256, 256, 0, st>>>(cg, n_cg, q, w.xact);
-                    PGPFA_LAUNCH_CHECK();
-                    PGPFA_TRY(pgpfa_i_solve32(w.LB32, w.DB32, w.pr, w.pz, 1.0, w.xact, T, n_cg * q, st, c0 * q));
-                    pgpfa_prof_end(h, st);
-                    h->prof_work[PGPFA_PROF_SOLVE] += (double)n_cg * blk_solve_bytes;
                     pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
+                    PGPFA_TRY(pgpfa_i_prior_apply(w.Minv, w.pr, w.pz, cg, n_cg, q, T, st));
                     PCG_DISPATCH(launch_pcg_dir, w.pr, w.pz, w.pp, cg, n_cg, T, ci == 0, w.pcg_s, st)
                     PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.pp, w.Kd, cg, n_cg, q, T, st));
                     PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, n_cg, T, w.pcg_s, w.conv, st)

@@ -12,8 +12,6 @@ struct PgpfaMatSrc {
     const double *dense;  // (slots, n, n)
     int q, T, n;
     double diag_scale;
-    int blk_q = 0;        // > 0: block-Jacobi systems M = Kinv_k + diag(W_kk), id = trial*blk_q + k, n = T, q = 1
-    int blk_base = 0;     // block-Jacobi factors are stored at (id - blk_base)
 };
 
 struct pgpfa_handle_s;
@@ -41,7 +39,7 @@ enum {
     PGPFA_PROF_EVAL = 2,      // prior mat-vec + fused rates/gradient/W + line search
     PGPFA_PROF_TRTRI = 3,     // triangular inverse; work = trials * n^3/3 flops
     PGPFA_PROF_SLICES = 4,    // time-diagonals + selected inverse tiles
-    PGPFA_PROF_BLOCKFACTOR = 5,  // block-Jacobi preconditioner factorisations (q T x T systems per trial)
+    PGPFA_PROF_BLOCKFACTOR = 5,  // CG preconditioner set-up (q shared T x T inverses per E-step)
     PGPFA_PROF_SLOTS = 8
 };
 struct PgpfaProfSpan { cudaEvent_t e0, e1; int slot; };
