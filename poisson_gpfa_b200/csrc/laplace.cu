@@ -18,12 +18,14 @@ using namespace pgpfa;
 
 namespace {
 
-// out[trial,k,s] = sum_t Kinv[k,s,t] v[trial,k,t]   (Kinv symmetric: read column-wise, coalesced)
-#define PA_TR 8
+// out[trial,k,s] = sum_t Kmat[k,s,t] v[trial,k,t]   (Kmat symmetric: read column-wise, coalesced).
+// One CTA = one latent x PA_TR trials: the T x T matrix is streamed from L2 once per PA_TR trials; the PA_TR
+// input vectors sit in shared memory as [t][trial] so that two trials come per 16-byte broadcast load.
+#define PA_TR 16
 __global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
                                                           double *__restrict__ out, const int *act, int nslots, int q,
                                                           int T) {
-    extern __shared__ double vs[];   // PA_TR x T
+    extern __shared__ __align__(16) double vs[];   // T x PA_TR
     __shared__ int trial[PA_TR];
     const int k = blockIdx.x;
     const int s0 = blockIdx.y * PA_TR;
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restri
     for (int i = threadIdx.x; i < PA_TR * T; i += blockDim.x) {
         const int r = i / T, t = i - r * T;
         const int tr = trial[r];
-        vs[i] = tr >= 0 ? v[((size_t)tr * q + k) * T + t] : 0.0;
+        vs[t * PA_TR + r] = tr >= 0 ? v[((size_t)tr * q + k) * T + t] : 0.0;
     }
     __syncthreads();
     const double *Kk = Kmat + (size_t)k * T * T;
@@ -45,8 +47,13 @@ __global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restri
         for (int r = 0; r < PA_TR; r++) acc[r] = 0.0;
         for (int t = 0; t < T; t++) {
             const double kv = Kk[(size_t)t * T + s];
+            const double2 *row = reinterpret_cast<const double2 *>(vs + t * PA_TR);
 #pragma unroll
-            for (int r = 0; r < PA_TR; r++) acc[r] += kv * vs[r * T + t];
+            for (int r2 = 0; r2 < PA_TR / 2; r2++) {
+                const double2 vv = row[r2];
+                acc[2 * r2] += kv * vv.x;
+                acc[2 * r2 + 1] += kv * vv.y;
+            }
         }
 #pragma unroll
         for (int r = 0; r < PA_TR; r++)
