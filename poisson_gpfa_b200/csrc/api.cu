@@ -97,6 +97,12 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
         delete h;
         return PGPFA_ERR_CUDA;
     }
+    h->s_half[0] = h->s_half[1] = nullptr;
+    PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_half[0], cudaStreamNonBlocking));
+    PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_half[1], cudaStreamNonBlocking));
+    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
+    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
     *out = h;
     return PGPFA_OK;
 }
@@ -104,6 +110,8 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
 extern "C" int pgpfa_destroy(pgpfa_handle_t h) {
     if (!h) return PGPFA_OK;
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->s_half[0]) { cudaStreamDestroy(h->s_half[0]); cudaStreamDestroy(h->s_half[1]); cudaEventDestroy(h->ev_fork);
+                        cudaEventDestroy(h->ev_join[0]); cudaEventDestroy(h->ev_join[1]); }
     delete h;
     return PGPFA_OK;
 }

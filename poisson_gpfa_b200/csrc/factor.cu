@@ -580,9 +580,8 @@ void launch_timediag(const double *ZT, const int *act, double *vsm, int nb, int 
 // =============================================================================================
 // internal host API (used by laplace.cu / mstep.cu / the C-ABI wrappers in api.cu)
 // =============================================================================================
-int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
-                   cudaStream_t st, pgpfa_handle_s *h, float *L32, float *D32) {
-    (void)h;
+static int factor_one(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
+                      cudaStream_t st, float *L32, float *D32) {
     if (nslots <= 0) return PGPFA_OK;
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
@@ -610,7 +609,7 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
     return PGPFA_OK;
 }
 
-int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st) {
+static int trtri_one(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st) {
     if (nslots <= 0) return PGPFA_OK;
     PGPFA_TRY(set_smem_attrs());
     FactorArgs a;
@@ -668,4 +667,51 @@ int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, do
     tiles_to_dense_kernel<<<grid, 256, 0, st>>>(tiles, pgpfa_nb(n), n, upper, out);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
+}
+
+// Large batches are split into two halves that run the same launch sequence on two streams: the partial last
+// wave of one half's launch is filled by CTAs of the other half instead of leaving SMs idle between steps.
+static bool split_streams(pgpfa_handle_s *h, int nslots, cudaStream_t st, cudaStream_t &sa, cudaStream_t &sb) {
+    if (!h || nslots < 512 || !h->s_half[0]) return false;
+    sa = h->s_half[0]; sb = h->s_half[1];
+    if (cudaEventRecord(h->ev_fork, st) != cudaSuccess) return false;
+    cudaStreamWaitEvent(sa, h->ev_fork, 0);
+    cudaStreamWaitEvent(sb, h->ev_fork, 0);
+    return true;
+}
+static int join_streams(pgpfa_handle_s *h, cudaStream_t st) {
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join[0], h->s_half[0]));
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join[1], h->s_half[1]));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[1], 0));
+    return PGPFA_OK;
+}
+
+int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
+                   cudaStream_t st, pgpfa_handle_s *h, float *L32, float *D32) {
+    cudaStream_t sa, sb;
+    if (ms.Kinv == nullptr || !split_streams(h, nslots, st, sa, sb))
+        return factor_one(ms, L, Dinv, ZT, act, info, nslots, st, L32, D32);
+    const int nb = pgpfa_nb(ms.n);
+    const size_t lt = (size_t)pgpfa_ltiles(nb) * PGPFA_TILE, dt = (size_t)nb * PGPFA_TILE;
+    const int h0 = nslots / 2, h1 = nslots - h0;
+    // generator mode only (W is indexed by trial id through act, so only the factor storage is offset)
+    int r0 = factor_one(ms, L, Dinv, ZT, act, info, h0, sa, L32, D32);
+    // the second half needs slot-relative storage: shift the base pointers, keep act entries (trial ids)
+    int r1 = factor_one(ms, L + h0 * lt, Dinv + h0 * dt, ZT ? ZT + h0 * lt : nullptr, act ? act + h0 : nullptr, info, h1, sb,
+                        L32 ? L32 + h0 * lt : nullptr, D32 ? D32 + h0 * dt : nullptr);
+    PGPFA_TRY(join_streams(h, st));
+    return r0 != PGPFA_OK ? r0 : r1;
+}
+
+int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st, pgpfa_handle_s *h) {
+    cudaStream_t sa, sb;
+    if (!split_streams(h, nslots, st, sa, sb)) return trtri_one(L, Dinv, ZT, n, nslots, st);
+    const int nb = pgpfa_nb(n);
+    const size_t lt = (size_t)pgpfa_ltiles(nb) * PGPFA_TILE, dt = (size_t)nb * PGPFA_TILE;
+    const int h0 = nslots / 2, h1 = nslots - h0;
+    int r0 = trtri_one(L, Dinv, ZT, n, h0, sa);
+    int r1 = trtri_one(L + h0 * lt, Dinv + h0 * dt, ZT + h0 * lt, n, h1, sb);
+    PGPFA_TRY(join_streams(h, st));
+    return r0 != PGPFA_OK ? r0 : r1;
 }

@@ -817,7 +817,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             polish_kernel<<<cn, 256, 0, st>>>(x, w.dx, w.actA, n, 1e3 * tol, w.steplen);
             PGPFA_LAUNCH_CHECK();
             pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);
-            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st));
+            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
             pgpfa_prof_end(h, st);
             h->prof_work[PGPFA_PROF_TRTRI] += (double)cn * n * (double)n * n / 3.0;
             pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);

@@ -17,7 +17,8 @@ struct PgpfaMatSrc {
 struct pgpfa_handle_s;
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
                    cudaStream_t st, pgpfa_handle_s *h = nullptr, float *L32 = nullptr, float *D32 = nullptr);
-int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st);
+int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st,
+                  pgpfa_handle_s *h = nullptr);
 int pgpfa_i_lauum(const double *ZT, const int2 *pairs, int npairs, const int *act, double *vsmGP, double *dense, int n,
                   int q, int T, int nslots, cudaStream_t st);
 int pgpfa_i_timediag(const double *ZT, const int *act, double *vsm, int n, int q, int T, int nslots, cudaStream_t st);
@@ -52,6 +53,8 @@ struct pgpfa_handle_s {
     double prof_work[PGPFA_PROF_SLOTS];
     long long prof_cnt[PGPFA_PROF_SLOTS];
     std::vector<PgpfaProfSpan> spans, open_spans;
+    cudaStream_t s_half[2];          // two streams for split batches (factor.cu)
+    cudaEvent_t ev_fork, ev_join[2];
 };
 void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
