@@ -222,6 +222,7 @@ def run_ours(args):
         h2d = (hi - lo) * N * T * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
         d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8
     e2e_sec = float(np.mean(e2e_t)) if e2e_t else float("nan")
+    print("e2e step times (s):", [round(t, 4) for t in e2e_t], file=sys.stderr)
     if world > 1:
         t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -97,18 +97,25 @@ int pgpfa_laplace_eval(const double *x, const double *y, const double *C, const 
 int pgpfa_hessian_dense(const double *Kinv, const double *W, double diag_scale, int R, int q, int T, double *H,
                         cudaStream_t stream);
 long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chunk);
-/* Batched Newton to ||step||_inf <= tol (1+||x||_inf) per trial, then posterior slices at the mode.
+/* Batched Laplace E-step (funs/inference.py:67-185): posterior mode to ||step||_inf <= tol (1+||x||_inf) per trial,
+ * then the posterior slices at the mode.
  * x: in = start (zeros or warm start, funs/inference.py:99-102), out = mode (post_mean).
- * reuse_factor != 0: the workspace still holds the factors left by the previous call for the SAME trials
- * (previous EM iteration); they drive cheap stale-factor (chord) iterations before any new factorisation,
- * with automatic per-trial fall-back to exact Newton.  Same fixed point, fewer factorisations.
- * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[8] = {trial-factorisations, max Newton
- * iterations, trials not converged, chunk size, chord iterations, trials that fell back to Newton,
- * factors kept (1/0), 0}. */
+ * flags bit 0: inexact Newton -- every Newton system is solved matrix-free by preconditioned conjugate gradients
+ * (one shared T x T preconditioner per latent), so the only qT x qT factorisation is the one at the mode; trials
+ * that struggle fall back per trial to exact Newton (fresh factorisation + chord sweeps), which is also what
+ * flags = 0 runs for every trial.  Same fixed point either way.
+ * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[8] = {trial-factorisations, max exact-Newton
+ * iterations, trials not converged, chunk size, inexact-Newton iterations, trials that fell back to exact Newton,
+ * whole batch in one chunk (1/0), chord sweeps + 1000 * CG iterations}. */
 int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
-                        double *x, int R, int q, int N, int T, double tol, int max_newton, int reuse_factor,
+                        double *x, int R, int q, int N, int T, double tol, int max_newton, int flags,
                         double *f_out, double *vsm, double *vsmGP, double *cov_dense, int *niter, int *info,
                         void *workspace, long long ws_bytes, int *stats_out, cudaStream_t stream);
+/* Makes `waiting_stream` wait for the point of the most recent pgpfa_laplace_solve on this handle after which x,
+ * f_out, vsm, niter and info are final; the selected-inverse tiles (vsmGP / cov_dense) of the last chunk may still
+ * be running on the solve's own stream.  Lets the C,d M-step (which needs only x and vsm, funs/learning.py:28-91)
+ * run on a second stream underneath the tensor-bound selected inverse.  No-op before the first solve. */
+int pgpfa_stream_wait_means(pgpfa_handle_t h, cudaStream_t waiting_stream);
 
 /* Leave-one-neuron-out prediction, funs/engine.py:599-644: problem p = (trial ymap[p], left-out neuron excl[p]);
  * the posterior mode is found without that neuron (x: P x q x T, in = start, out = mode) and its rate predicted:

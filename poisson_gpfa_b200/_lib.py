@@ -23,6 +23,7 @@ SIGNATURES = {
     "pgpfa_error_string": (ctypes.c_char_p, [c_int]),
     "pgpfa_last_cuda_error": (ctypes.c_char_p, []),
     "pgpfa_launch_count": (c_ll, []),
+    "pgpfa_stream_wait_means": (c_int, [c_void_p, c_void_p]),
     "pgpfa_set_profiling": (c_int, [c_void_p, c_int]),
     "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
     "pgpfa_map": (c_int, [c_int, c_ll, P, P, c_dbl, P, P]),

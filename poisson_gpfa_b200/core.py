@@ -5,14 +5,16 @@ Newton E-step (funs/inference.py:67-185), ``mstep_cd`` the per-neuron Newton on 
 (funs/learning.py:93-141 / :536-676 'useDiag'), ``mstep_tau`` the timescale update
 (funs/learning.py:257-293 / :771-830).  Cross-rank reductions go through ``dist.Reducer``.
 """
+import contextlib
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import _lib, kernels as kn
-from ._lib import call, empty, ptr, stream
+from ._lib import call, empty, handle, ptr, stream
 from .dist import Reducer
 
 EPS_NOISE = 0.001   # funs/util.py:599, funs/learning.py:286
@@ -63,6 +65,11 @@ class EStepResult:
         self.x, self.f, self.vsm, self.vsmGP = x, f, vsm, vsmGP
         self.niter, self.stats = niter, stats
         self.params, self.trials = params, trials
+        self.side = None      # stream on which x / f / vsm are complete while vsmGP may still be in flight on the main one
+
+    def means_stream(self):
+        """Context in which work that needs only x, f and vsm runs: the side stream if the E-step left one."""
+        return torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
 
 
 class DeviceTrials:
@@ -80,6 +87,18 @@ class DeviceTrials:
         self._lap_ws = None
         self._cd_ws = None
         self._tau_ws = None
+        self._side = None
+
+    def _means_stream(self):
+        """High-priority stream ordered after the point of the last Laplace solve where the posterior means and
+        time-diagonal covariances are final (pgpfa_stream_wait_means): the info check, the objective and the C,d
+        M-step run there, underneath the selected-inverse kernel that is still producing post_vsmGP."""
+        if os.environ.get("PGPFA_SIDE_STREAM", "1") == "0":      # debugging switch: everything on the caller's stream
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(priority=-1)
+        call("pgpfa_stream_wait_means", handle(), self._side.cuda_stream)
+        return self._side
 
     # ------------------------------------------------------------------ E-step
     def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True):
@@ -93,10 +112,13 @@ class DeviceTrials:
             self._lap_ws = ((R, q, T), _lib.workspace(nbytes))
         res = kn.laplace_solve(self.y, params.C, params.d, params.Kinv, x0=x0, tol=tol, max_newton=max_newton,
                                want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton)
-        if int(res.info.abs().max()) != 0:
-            raise FloatingPointError("posterior Hessian not positive definite for %d trial(s)"
-                                     % int((res.info != 0).sum()))
-        return EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
+        est = EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
+        est.side = self._means_stream()
+        with est.means_stream():
+            if int(res.info.abs().max()) != 0:
+                raise FloatingPointError("posterior Hessian not positive definite for %d trial(s)"
+                                         % int((res.info != 0).sum()))
+        return est
 
     def estep_variational(self, params, lam0=None, tol=1e-10, max_iter=300, want_vsmGP=True):
         """Dual variational E-step (funs/inference.py:259-432): the stationary point of the dual for every
@@ -115,7 +137,8 @@ class DeviceTrials:
 
     def post_lik(self, est):
         """-mean_r L(x_r*) over ALL trials (funs/inference.py:175,183)."""
-        return -self.reducer.sum_scalar(float(est.f.sum())) / self.R_total
+        with est.means_stream():
+            return -self.reducer.sum_scalar(float(est.f.sum())) / self.R_total
 
     # ------------------------------------------------------------------ M-step C,d
     def mstep_cd(self, params, est, prior_w=0.0, tol=1e-10, max_iter=100, one_step=False, step_size=1.0,
@@ -123,36 +146,43 @@ class DeviceTrials:
         """Per-neuron damped Newton on MStepObservationCost (+ 0.5*prior_w*|theta-theta_old|^2).
         Returns (C, d, cost, iterations).  `one_step`: a single (scaled) Newton step from the old
         parameters, the 'grad' online rule of funs/learning.py:884-891 with the analytic Hessian."""
-        N, q = params.C.shape
-        P = q + 1
-        theta0 = params.theta
-        th_cur, th_try = theta0.clone(), theta0.clone()
-        fcur, alpha, slope = empty(N), empty(N), empty(N)
-        step = empty(N, P)
-        done = torch.zeros(N, dtype=torch.int32, device="cuda")
-        n_open = torch.zeros(1, dtype=torch.int32, device="cuda")
-        if self._cd_ws is None or self._cd_ws[0] != (q, N):
-            self._cd_ws = ((q, N), _lib.workspace(_lib.lib.pgpfa_mstep_cd_workspace_bytes(q, N)))
-        inv_R = 1.0 / self.R_total
-        it = 0
-        hess = None
-        for it in range(1, max_iter + 1):
-            stats = kn.mstep_cd_stats(self.y, est.x, est.vsm, th_try, ws=self._cd_ws[1])
-            stats = self.reducer.sum_tensor(stats)
-            if one_step:
-                hess = stats
+        main = torch.cuda.current_stream()
+        with est.means_stream():
+            N, q = params.C.shape
+            P = q + 1
+            theta0 = params.theta
+            th_cur, th_try = theta0.clone(), theta0.clone()
+            fcur, alpha, slope = empty(N), empty(N), empty(N)
+            step = empty(N, P)
+            done = torch.zeros(N, dtype=torch.int32, device="cuda")
+            n_open = torch.zeros(1, dtype=torch.int32, device="cuda")
+            if self._cd_ws is None or self._cd_ws[0] != (q, N):
+                self._cd_ws = ((q, N), _lib.workspace(_lib.lib.pgpfa_mstep_cd_workspace_bytes(q, N)))
+            inv_R = 1.0 / self.R_total
+            it = 0
+            hess = None
+            for it in range(1, max_iter + 1):
+                stats = kn.mstep_cd_stats(self.y, est.x, est.vsm, th_try, ws=self._cd_ws[1])
+                stats = self.reducer.sum_tensor(stats)
+                if one_step:
+                    hess = stats
+                    call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
+                         ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open),
+                         stream())
+                    th_cur = kn.emap("axpy", theta0, step, step_size)
+                    break
                 call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
-                     ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open),
-                     stream())
-                th_cur = kn.emap("axpy", theta0, step, step_size)
-                break
-            call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
-                 ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol),
-                 N, q, ptr(n_open), stream())
-            if int(n_open.item()) == 0:
-                break
-        cost = float(fcur.sum())
-        return th_cur[:, :q].contiguous(), th_cur[:, q].contiguous(), cost, it, hess
+                     ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol),
+                     N, q, ptr(n_open), stream())
+                if int(n_open.item()) == 0:
+                    break
+            cost = float(fcur.sum())
+            C_new, d_new = th_cur[:, :q].contiguous(), th_cur[:, q].contiguous()
+        if est.side is not None:                 # results were produced on the side stream: order the main one after it
+            main.wait_stream(est.side)
+            for t in (C_new, d_new) + ((hess,) if hess is not None else ()):
+                t.record_stream(main)
+        return C_new, d_new, cost, it, hess
 
     def cd_cost_grad(self, theta, est):
         """(cost, grad (N,q+1)) of MStepObservationCost at theta, normalised by the global trial count."""

@@ -46,6 +46,12 @@ void pgpfa_prof_resolve(pgpfa_handle_t h) {   // call after a stream synchronise
     h->spans.clear();
 }
 
+extern "C" int pgpfa_stream_wait_means(pgpfa_handle_t h, cudaStream_t waiting_stream) {
+    if (!h) return PGPFA_ERR_ARG;
+    PGPFA_CUDA_TRY(cudaStreamWaitEvent(waiting_stream, h->ev_means, 0));
+    return PGPFA_OK;
+}
+
 extern "C" int pgpfa_set_profiling(pgpfa_handle_t h, int on) {
     if (!h) return PGPFA_ERR_ARG;
     h->profiling = on != 0;
@@ -97,12 +103,13 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
         delete h;
         return PGPFA_ERR_CUDA;
     }
-    h->s_half[0] = h->s_half[1] = nullptr;
-    PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_half[0], cudaStreamNonBlocking));
-    PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_half[1], cudaStreamNonBlocking));
+    for (int p = 0; p < PGPFA_MAX_PARTS; p++) h->s_part[p] = nullptr;
     PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
-    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
+    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_means, cudaEventDisableTiming));
+    for (int p = 0; p < PGPFA_MAX_PARTS; p++) {
+        PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming));
+        PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_part[p], cudaStreamNonBlocking));
+    }
     *out = h;
     return PGPFA_OK;
 }
@@ -110,8 +117,14 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
 extern "C" int pgpfa_destroy(pgpfa_handle_t h) {
     if (!h) return PGPFA_OK;
     if (h->pinned) cudaFreeHost(h->pinned);
-    if (h->s_half[0]) { cudaStreamDestroy(h->s_half[0]); cudaStreamDestroy(h->s_half[1]); cudaEventDestroy(h->ev_fork);
-                        cudaEventDestroy(h->ev_join[0]); cudaEventDestroy(h->ev_join[1]); }
+    if (h->s_part[0]) {
+        cudaEventDestroy(h->ev_fork);
+        cudaEventDestroy(h->ev_means);
+        for (int p = 0; p < PGPFA_MAX_PARTS; p++) {
+            if (h->s_part[p]) cudaStreamDestroy(h->s_part[p]);
+            cudaEventDestroy(h->ev_join[p]);
+        }
+    }
     delete h;
     return PGPFA_OK;
 }

@@ -314,7 +314,7 @@ extern "C" int pgpfa_dualvi_eval(pgpfa_handle_t h, const double *lam, const doub
         vi_dual_value_kernel<<<cn, 256, 0, st>>>(w.v, w.Kv, w.sums, w.logdet, w.actA, n, D, mean);
         PGPFA_LAUNCH_CHECK();
         if (grad || vsm || cov_dense) {
-            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st));
+            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
             if (cov_dense)
                 PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, nullptr,
@@ -365,7 +365,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
                                          niter, w.steplen, -1, st, s));
-            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, n_act, st));
+            PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, n_act, st, h));
             PGPFA_TRY(pgpfa_i_timediag(w.ZT, act, vsm, n, q, T, n_act, st));
             VI_DISPATCH(vi_s_update_kernel, n_act, (size_t)N * q * sizeof(double), vsm, C, s, act, N, T, tol, w.conv, w.dsmax)
             PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 1, act_next, w.cnt, st));
@@ -385,7 +385,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
         PGPFA_TRY(pgpfa_i_logdet(w.L, n, cn, w.logdet, st));
         vi_dual_value_kernel<<<cn, 256, 0, st>>>(w.v, w.Kv, w.sums, w.logdet, w.actA, n, D, mean);
         PGPFA_LAUNCH_CHECK();
-        PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st));
+        PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
         PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
         if (vsmGP || cov_dense)
             PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,

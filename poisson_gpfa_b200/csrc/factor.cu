@@ -108,7 +108,7 @@ __device__ __forceinline__ void diag8_factor(double *S, double *DI, int *bad_sm,
     const int i = lane & 7;
     double a[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) a[c] = (c <= i) ? S[(8 * b + i) * SLD + 8 * b + c] : 0.0;
+    for (int c = 0; c < 8; c++) a[c] = (lane < 8 && c <= i) ? S[(8 * b + i) * SLD + 8 * b + c] : 0.0;   // lanes 8-31 only relay shuffles
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         double piv = __shfl_sync(0xffffffffu, a[k], k);
@@ -669,49 +669,70 @@ int pgpfa_i_tiles_to_dense(const double *tiles, int n, int upper, int nslots, do
     return PGPFA_OK;
 }
 
-// Large batches are split into two halves that run the same launch sequence on two streams: the partial last
-// wave of one half's launch is filled by CTAs of the other half instead of leaving SMs idle between steps.
-static bool split_streams(pgpfa_handle_s *h, int nslots, cudaStream_t st, cudaStream_t &sa, cudaStream_t &sb) {
-    if (!h || nslots < 512 || !h->s_half[0]) return false;
-    sa = h->s_half[0]; sb = h->s_half[1];
-    if (cudaEventRecord(h->ev_fork, st) != cudaSuccess) return false;
-    cudaStreamWaitEvent(sa, h->ev_fork, 0);
-    cudaStreamWaitEvent(sb, h->ev_fork, 0);
-    return true;
+// Large batches are split into parts that run the same launch sequence on separate streams: the partial last
+// wave (and the serial diagonal-tile work) of one part's launch is filled by CTAs of the others instead of leaving
+// SMs idle between steps.  PGPFA_SPLIT=k overrides the number of parts (1 = off).
+static int split_parts(pgpfa_handle_s *h, int nslots) {
+    if (!h || !h->s_part[0]) return 1;
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("PGPFA_SPLIT"); forced = e ? atoi(e) : 0; }
+    int parts = forced > 0 ? forced : (nslots >= 512 ? 2 : nslots >= 64 ? 4 : 1);
+    if (parts > PGPFA_MAX_PARTS) parts = PGPFA_MAX_PARTS;
+    if (parts > nslots) parts = nslots > 0 ? nslots : 1;
+    return parts;
 }
-static int join_streams(pgpfa_handle_s *h, cudaStream_t st) {
-    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join[0], h->s_half[0]));
-    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join[1], h->s_half[1]));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[0], 0));
-    PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[1], 0));
+static int fork_streams(pgpfa_handle_s *h, int parts, cudaStream_t st) {
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    for (int p = 0; p < parts; p++) PGPFA_CUDA_TRY(cudaStreamWaitEvent(h->s_part[p], h->ev_fork, 0));
+    return PGPFA_OK;
+}
+static int join_streams(pgpfa_handle_s *h, int parts, cudaStream_t st) {
+    for (int p = 0; p < parts; p++) {
+        PGPFA_CUDA_TRY(cudaEventRecord(h->ev_join[p], h->s_part[p]));
+        PGPFA_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[p], 0));
+    }
     return PGPFA_OK;
 }
 
 int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, const int *act, int *info, int nslots,
                    cudaStream_t st, pgpfa_handle_s *h, float *L32, float *D32) {
-    cudaStream_t sa, sb;
-    if (ms.Kinv == nullptr || !split_streams(h, nslots, st, sa, sb))
-        return factor_one(ms, L, Dinv, ZT, act, info, nslots, st, L32, D32);
+    const int parts = split_parts(h, nslots);
+    if (parts <= 1) return factor_one(ms, L, Dinv, ZT, act, info, nslots, st, L32, D32);
     const int nb = pgpfa_nb(ms.n);
     const size_t lt = (size_t)pgpfa_ltiles(nb) * PGPFA_TILE, dt = (size_t)nb * PGPFA_TILE;
-    const int h0 = nslots / 2, h1 = nslots - h0;
-    // generator mode only (W is indexed by trial id through act, so only the factor storage is offset)
-    int r0 = factor_one(ms, L, Dinv, ZT, act, info, h0, sa, L32, D32);
-    // the second half needs slot-relative storage: shift the base pointers, keep act entries (trial ids)
-    int r1 = factor_one(ms, L + h0 * lt, Dinv + h0 * dt, ZT ? ZT + h0 * lt : nullptr, act ? act + h0 : nullptr, info, h1, sb,
-                        L32 ? L32 + h0 * lt : nullptr, D32 ? D32 + h0 * dt : nullptr);
-    PGPFA_TRY(join_streams(h, st));
-    return r0 != PGPFA_OK ? r0 : r1;
+    PGPFA_TRY(fork_streams(h, parts, st));
+    int rc = PGPFA_OK;
+    for (int p = 0; p < parts; p++) {
+        const int s0 = (int)((long long)nslots * p / parts), s1 = (int)((long long)nslots * (p + 1) / parts);
+        // factor storage is slot-indexed: shift the bases.  With an active list the matrix source and info stay
+        // trial-indexed through act; without one trial == slot, so they are shifted as well.
+        PgpfaMatSrc m = ms;
+        int *inf = info;
+        if (!act) {
+            if (m.W) m.W += (size_t)s0 * ms.q * ms.q * ms.T;
+            if (m.dense) m.dense += (size_t)s0 * ms.n * ms.n;
+            if (inf) inf += s0;
+        }
+        const int r = factor_one(m, L + s0 * lt, Dinv + s0 * dt, ZT ? ZT + s0 * lt : nullptr, act ? act + s0 : nullptr, inf,
+                                 s1 - s0, h->s_part[p], L32 ? L32 + s0 * lt : nullptr, D32 ? D32 + s0 * dt : nullptr);
+        if (rc == PGPFA_OK) rc = r;
+    }
+    PGPFA_TRY(join_streams(h, parts, st));
+    return rc;
 }
 
 int pgpfa_i_trtri(const double *L, const double *Dinv, double *ZT, int n, int nslots, cudaStream_t st, pgpfa_handle_s *h) {
-    cudaStream_t sa, sb;
-    if (!split_streams(h, nslots, st, sa, sb)) return trtri_one(L, Dinv, ZT, n, nslots, st);
+    const int parts = split_parts(h, nslots);
+    if (parts <= 1) return trtri_one(L, Dinv, ZT, n, nslots, st);
     const int nb = pgpfa_nb(n);
     const size_t lt = (size_t)pgpfa_ltiles(nb) * PGPFA_TILE, dt = (size_t)nb * PGPFA_TILE;
-    const int h0 = nslots / 2, h1 = nslots - h0;
-    int r0 = trtri_one(L, Dinv, ZT, n, h0, sa);
-    int r1 = trtri_one(L + h0 * lt, Dinv + h0 * dt, ZT + h0 * lt, n, h1, sb);
-    PGPFA_TRY(join_streams(h, st));
-    return r0 != PGPFA_OK ? r0 : r1;
+    PGPFA_TRY(fork_streams(h, parts, st));
+    int rc = PGPFA_OK;
+    for (int p = 0; p < parts; p++) {
+        const int s0 = (int)((long long)nslots * p / parts), s1 = (int)((long long)nslots * (p + 1) / parts);
+        const int r = trtri_one(L + s0 * lt, Dinv + s0 * dt, ZT + s0 * lt, n, s1 - s0, h->s_part[p]);
+        if (rc == PGPFA_OK) rc = r;
+    }
+    PGPFA_TRY(join_streams(h, parts, st));
+    return rc;
 }

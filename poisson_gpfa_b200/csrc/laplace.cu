@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
 
 // ---------------------------------------------------------------------------------------------
 // Batched preconditioned conjugate gradients for the Newton systems H(x) delta = -g, H v = Kinv v + W v
-// (per-bin q x q blocks), preconditioner = the factor kept from the previous E-step (FP32 mirror).
+// (per-bin q x q blocks); the preconditioner z = M^-1 r is applied by the caller (prior_apply with the shared
+// per-latent T x T inverses).
 // One CTA per trial; the per-trial scalars live in pcg_s[trial*4 + {rz, bnorm2, eta, unused}].
 // ---------------------------------------------------------------------------------------------
 template <int Q>
@@ -396,6 +397,10 @@ __global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict_
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     const size_t base = (size_t)trial * Q * T;
     const double *Wt = W + (size_t)trial * Q * Q * T;
+    if (pcg_s[trial * 4 + 1] == 0.0) {           // zero gradient: delta = 0 is exact (pcg_init flagged it converged)
+        if (threadIdx.x == 0) conv[trial] = 1;
+        return;
+    }
     double pHp = 0.0;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         double pk[Q];
@@ -822,6 +827,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             h->prof_work[PGPFA_PROF_TRTRI] += (double)cn * n * (double)n * n / 3.0;
             pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
+            PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
             if (vsmGP || cov_dense)
                 PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,
                                         cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));

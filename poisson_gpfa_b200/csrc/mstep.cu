@@ -240,18 +240,21 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
     }
 }
 
-// C = A * B for a batch of row-major n x n matrices (small FP64 GEMM, 64x64 tiles, 16x16 threads)
-__global__ void __launch_bounds__(256) small_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
+// C = A * B for a batch of row-major n x n matrices on the FP64 tensor pipe (DMMA.8x8x4): CTA = 64x64 tile of C,
+// 4 warps as 2x2 of 32x32, k in chunks of 16 staged through padded shared memory (conflict-free fragment loads:
+// A stride 20 and B stride 68 doubles put the 16 lanes of a half-warp on 16 distinct 8-byte banks).
+__global__ void __launch_bounds__(128) small_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                          double *__restrict__ Cm, int n) {
-    __shared__ double As[64][17], Bs[16][65];
+    __shared__ double As[64][20], Bs[16][68];
     const int b = blockIdx.z;
     const double *Ab = A + (size_t)b * n * n, *Bb = B + (size_t)b * n * n;
     double *Cb = Cm + (size_t)b * n * n;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    double acc[4][4] = {};
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][2] = {};
     for (int k0 = 0; k0 < n; k0 += 16) {
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        for (int i = tid; i < 64 * 16; i += 128) {
             const int rr = i >> 4, kk = i & 15;
             As[rr][kk] = (r0 + rr < n && k0 + kk < n) ? Ab[(size_t)(r0 + rr) * n + k0 + kk] : 0.0;
             const int k2 = i >> 6, cc = i & 63;
@@ -259,26 +262,28 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const double *__restric
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
+        for (int k4 = 0; k4 < 16; k4 += 4) {
             double a[4], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[ty * 4 + i][kk];
+            for (int i = 0; i < 4; i++) a[i] = As[wm * 32 + i * 8 + fr][k4 + fk];
 #pragma unroll
-            for (int j = 0; j < 4; j++) bb[j] = Bs[kk][tx * 4 + j];
+            for (int j = 0; j < 4; j++) bb[j] = Bs[k4 + fk][wn * 32 + j * 8 + fr];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] += a[i] * bb[j];
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
-            if (r < n && c < n) Cb[(size_t)r * n + c] = acc[i][j];
-        }
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int r = r0 + wm * 32 + i * 8 + fr, c = c0 + wn * 32 + j * 8 + 2 * fk + e;
+                if (r < n && c < n) Cb[(size_t)r * n + c] = acc[i][j][e];
+            }
 }
 
 // cost / gradient of the timescale objective from Kinv, logdet, dK, G = Kinv dK Kinv and PautoSum
@@ -406,9 +411,9 @@ extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTri
     PGPFA_TRY(pgpfa_make_K_gamma(p, q, T, eps, K, dK, st));
     PGPFA_TRY(pgpfa_spd_inverse_batched(K, q, T, Kinv, logdet, info, w, inv_bytes, st));
     dim3 grid((T + 63) / 64, (T + 63) / 64, q);
-    small_gemm_kernel<<<grid, 256, 0, st>>>(Kinv, dK, M1, T);
+    small_gemm_kernel<<<grid, 128, 0, st>>>(Kinv, dK, M1, T);
     PGPFA_LAUNCH_CHECK();
-    small_gemm_kernel<<<grid, 256, 0, st>>>(M1, Kinv, G, T);
+    small_gemm_kernel<<<grid, 128, 0, st>>>(M1, Kinv, G, T);
     PGPFA_LAUNCH_CHECK();
     tau_reduce_kernel<<<q, 256, 0, st>>>(p, Kinv, dK, G, Psum, logdet, numTrials, T, prior_w, tau_old, bs, cost, grad);
     PGPFA_LAUNCH_CHECK();

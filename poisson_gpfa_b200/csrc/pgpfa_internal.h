@@ -43,6 +43,7 @@ enum {
     PGPFA_PROF_BLOCKFACTOR = 5,  // CG preconditioner set-up (q shared T x T inverses per E-step)
     PGPFA_PROF_SLOTS = 8
 };
+#define PGPFA_MAX_PARTS 4
 struct PgpfaProfSpan { cudaEvent_t e0, e1; int slot; };
 
 struct pgpfa_handle_s {
@@ -53,8 +54,9 @@ struct pgpfa_handle_s {
     double prof_work[PGPFA_PROF_SLOTS];
     long long prof_cnt[PGPFA_PROF_SLOTS];
     std::vector<PgpfaProfSpan> spans, open_spans;
-    cudaStream_t s_half[2];          // two streams for split batches (factor.cu)
-    cudaEvent_t ev_fork, ev_join[2];
+    cudaStream_t s_part[PGPFA_MAX_PARTS];   // streams for split batches (factor.cu)
+    cudaEvent_t ev_fork, ev_join[PGPFA_MAX_PARTS];
+    cudaEvent_t ev_means;                   // recorded after the time-diagonal kernel of a Laplace solve
 };
 void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
