@@ -205,7 +205,8 @@ def run_ours(args):
     e2e_t = []
     h2d = d2h = 0
     exp = inference_experiment(Y_pin, w)
-    for i in range(e2e_steps + 1 if e2e_steps else 0):
+    E2E_WARMUP = 2                                         # untimed: allocate the API path's own buffers, settle the host
+    for i in range(e2e_steps + E2E_WARMUP if e2e_steps else 0):
         barrier()
         t0 = time.perf_counter()
         inference.upload_counts(exp)                       # H2D of this step's inputs (pinned -> HBM)
@@ -217,7 +218,7 @@ def run_ours(args):
         host_params, det = learning.updateParams(host_params, infRes, exp)
         modes_host = optim.tensor.cpu().numpy()            # D2H of the step's results
         barrier()
-        if i > 0:
+        if i >= E2E_WARMUP:
             e2e_t.append(time.perf_counter() - t0)
         h2d = (hi - lo) * N * T * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
         d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8

@@ -90,6 +90,8 @@ int pgpfa_logdet(const double *L_tiles, int batch, int n, double *logdet, cudaSt
 int pgpfa_tiles_to_dense(const double *tiles, int batch, int n, int upper, double *out, cudaStream_t stream);
 
 /* ---- (2) Laplace E-step: funs/inference.py:12-185 -------------------------------------------- */
+/* out[r][k][s] = sum_t Kmat[k][s][t] v[r][k][t]: one T x T matrix per latent (row-major, need not be symmetric)
+ * applied to every trial (K^-1 x in funs/inference.py:16-17, and chol(K) z when sampling). */
 int pgpfa_prior_apply(const double *Kmat, const double *v, int R, int q, int T, double *out, cudaStream_t stream);
 /* f[r], g[r][k][t], W[r][kl][t] at given x; Kx_ws is an R*q*T scratch (receives Kinv x) */
 int pgpfa_laplace_eval(const double *x, const double *y, const double *C, const double *d, const double *Kinv, int R,

@@ -18,47 +18,81 @@ using namespace pgpfa;
 
 namespace {
 
-// out[trial,k,s] = sum_t Kmat[k,s,t] v[trial,k,t]   (Kmat symmetric: read column-wise, coalesced).
-// One CTA = one latent x PA_TR trials: the T x T matrix is streamed from L2 once per PA_TR trials; the PA_TR
-// input vectors sit in shared memory as [t][trial] so that two trials come per 16-byte broadcast load.
-#define PA_TR 16
-__global__ void __launch_bounds__(256) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
+// out[trial,k,s] = sum_t Kmat[k,s,t] v[trial,k,t]: per latent a (T x T) x (T x trials) product, on the FP64 tensor
+// pipe (DMMA.8x8x4).  CTA = 64 rows (s) x 32 trials of one latent, 4 warps as 2x2 of 32x16; t in chunks of 16
+// through double-buffered padded shared memory (strides 20 / 36 doubles keep the 16 lanes of a half-warp on distinct
+// 8-byte banks), the next chunk's global loads are issued before the MMAs of the current one.  The matrices stay
+// in L2 (q T^2 doubles); the vectors are gathered through the active list.
+#define PA_TS 64
+#define PA_TN 32
+__global__ void __launch_bounds__(128) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
                                                           double *__restrict__ out, const int *act, int nslots, int q,
                                                           int T) {
-    extern __shared__ __align__(16) double vs[];   // T x PA_TR
-    __shared__ int trial[PA_TR];
-    const int k = blockIdx.x;
-    const int s0 = blockIdx.y * PA_TR;
-    if (threadIdx.x < PA_TR) {
-        const int slot = s0 + threadIdx.x;
-        trial[threadIdx.x] = slot < nslots ? (act ? act[slot] : slot) : -1;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PA_TR * T; i += blockDim.x) {
-        const int r = i / T, t = i - r * T;
-        const int tr = trial[r];
-        vs[t * PA_TR + r] = tr >= 0 ? v[((size_t)tr * q + k) * T + t] : 0.0;
+    __shared__ double As[2][PA_TS][20];
+    __shared__ double Bs[2][16][36];
+    __shared__ int trial[PA_TN];
+    const int k = blockIdx.x, s0 = blockIdx.y * PA_TS, n0 = blockIdx.z * PA_TN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const int fr = lane >> 2, fk = lane & 3;
+    if (tid < PA_TN) {
+        const int slot = n0 + tid;
+        trial[tid] = slot < nslots ? (act ? act[slot] : slot) : -1;
     }
     __syncthreads();
     const double *Kk = Kmat + (size_t)k * T * T;
-    for (int s = threadIdx.x; s < T; s += blockDim.x) {
-        double acc[PA_TR];
+    // this thread's share of a chunk: 8 elements of A (row ar + 8 j, column ac), 4 of B (trial bn + 8 j, bin bc)
+    const int ar = tid >> 4, ac = tid & 15, bn = tid >> 4, bc = tid & 15;
+    const double *bsrc[4];
 #pragma unroll
-        for (int r = 0; r < PA_TR; r++) acc[r] = 0.0;
-        for (int t = 0; t < T; t++) {
-            const double kv = Kk[(size_t)t * T + s];
-            const double2 *row = reinterpret_cast<const double2 *>(vs + t * PA_TR);
+    for (int jj = 0; jj < 4; jj++) {
+        const int tr = trial[bn + 8 * jj];
+        bsrc[jj] = tr >= 0 ? v + ((size_t)tr * q + k) * T : nullptr;
+    }
+    double ra[8], rb[4];
+    auto fetch = [&](int t0) {
+        const bool tc = t0 + ac < T;
 #pragma unroll
-            for (int r2 = 0; r2 < PA_TR / 2; r2++) {
-                const double2 vv = row[r2];
-                acc[2 * r2] += kv * vv.x;
-                acc[2 * r2 + 1] += kv * vv.y;
-            }
+        for (int jj = 0; jj < 8; jj++) {
+            const int s = s0 + ar + 8 * jj;
+            ra[jj] = (tc && s < T) ? Kk[(size_t)s * T + t0 + ac] : 0.0;
         }
 #pragma unroll
-        for (int r = 0; r < PA_TR; r++)
-            if (trial[r] >= 0) out[((size_t)trial[r] * q + k) * T + s] = acc[r];
+        for (int jj = 0; jj < 4; jj++) rb[jj] = (bsrc[jj] && t0 + bc < T) ? bsrc[jj][t0 + bc] : 0.0;
+    };
+    double acc[4][2][2] = {};
+    const int mblocks = min(4, (T - s0 - wm * 32 + 7) / 8);      // 8-row blocks of this warp that hold rows < T
+    fetch(0);
+    int buf = 0;
+    for (int t0 = 0; t0 < T; t0 += 16, buf ^= 1) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) As[buf][ar + 8 * jj][ac] = ra[jj];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) Bs[buf][bc][bn + 8 * jj] = rb[jj];
+        __syncthreads();
+        if (t0 + 16 < T) fetch(t0 + 16);
+#pragma unroll
+        for (int k4 = 0; k4 < 16; k4 += 4) {
+            double b0 = Bs[buf][k4 + fk][wn * 16 + fr], b1 = Bs[buf][k4 + fk][wn * 16 + 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i < mblocks) {
+                    const double a = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
+                    dmma884(acc[i][0][0], acc[i][0][1], a, b0);
+                    dmma884(acc[i][1][0], acc[i][1][1], a, b1);
+                }
+            }
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jn = 0; jn < 2; jn++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int s = s0 + wm * 32 + i * 8 + fr;
+                const int tr = trial[wn * 16 + jn * 8 + 2 * fk + e];
+                if (s < T && tr >= 0) out[((size_t)tr * q + k) * T + s] = acc[i][jn][e];
+            }
 }
 
 // fused rates + objective + gradient + per-bin Hessian blocks; one CTA per trial, thread <-> bin
@@ -134,7 +168,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
     const double *__restrict__ d, const double *__restrict__ off, const int *act, int N, int T, double tol,
     double *__restrict__ fcur, int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen,
-    int chord_it, LooMap loo, double *__restrict__ pcg_s) {
+    int step_kind, LooMap loo, double *__restrict__ pcg_s) {
     extern __shared__ double sm[];
     double *Cs = sm;
     double *ds = sm + N * Q;
@@ -196,37 +230,28 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     if (threadIdx.x == 0) {
         fcur[trial] = fnew;
         const double sl = alpha * dmax;
-        // state: 0 keep iterating, 1 converged, 2 stale-factor (chord) iteration contracts too slowly ->
-        // hand the trial to the exact-Newton loop
-        // chord_it encodes the kind of step that was just taken:
-        //   -1-k           exact Newton step k (fresh factor at this x).  Quadratic convergence: with
-        //                  c ~ sl_k / sl_{k-1}^2 the error after this step is ~ sl_k^3 / sl_{k-1}^2.
-        //   0..999         stale-factor (previous EM iteration) chord sweep: only has to reach Newton's fast regime.
-        //   1000+k         chord sweep k with the factor computed earlier in THIS call (at a point ~1e-2 from the
-        //                  mode): contraction ~ |H(x_f)^-1 (H(x_f) - H(x*))| ~ 1e-2 per sweep, replaces re-factorising.
+        // step_kind encodes the kind of step that was just taken:
+        //   -1-k      exact Newton step k (fresh factor at this x).  Quadratic convergence: with
+        //             c ~ sl_k / sl_{k-1}^2 the error after this step is ~ sl_k^3 / sl_{k-1}^2.
+        //   1000+k    chord sweep k with the factor computed earlier in this call (at a point ~1e-2 from the mode):
+        //             contraction ~ |H(x_f)^-1 (H(x_f) - H(x*))| ~ 1e-2 per sweep, replaces re-factorising.
+        //   2000+k    inexact Newton step k (direction from PCG at relative residual eta).
         // states: 0 keep going with the same kind of step, 1 converged, 2 needs a fresh factorisation.
         int state;
         const double scale = 1.0 + xmax;
         const double prev = steplen[trial];
-        if (chord_it < 0) {
+        if (step_kind < 0) {
             state = (sl <= tol * scale) ? 1 : 0;
-            if (state == 0 && chord_it <= -2 && alpha == 1.0 && prev > 0.0 && sl < 0.1 * prev &&
+            if (state == 0 && step_kind <= -2 && alpha == 1.0 && prev > 0.0 && sl < 0.1 * prev &&
                 sl * sl * sl / (prev * prev) <= 0.1 * tol * scale)
                 state = 1;
-        } else if (chord_it < 1000) {
-            const double chord_goal = 1e-2;
-            state = (sl <= chord_goal * scale) ? 2 : 0;
-            if (state == 0 && chord_it >= 1 && sl > 0.7 * prev) state = 2;
-            // already converged (late EM: parameters barely move): certified by the observed contraction
-            if (chord_it >= 1 && sl < 0.5 * prev && sl * (sl / prev) / (1.0 - sl / prev) <= tol * scale) state = 1;
-            if (chord_it == 0 && sl <= 0.01 * tol * scale) state = 1;
-        } else if (chord_it >= 2000) {
-            // inexact Newton (PCG to relative residual eta): error after this step ~ c sl^2 + 2 eta sl.
-            // The next solve is asked for eta' ~ 0.1 * (relative step just taken): superlinear overall.
+        } else if (step_kind >= 2000) {
+            // error after this step ~ c sl^2 + 2 eta sl.  The next solve is asked for
+            // eta' = 0.03 * (relative step just taken): superlinear overall.
             const double eta = pcg_s[trial * 4 + 2];
             const double rel = sl / scale;
             state = (0.2 * rel * rel + 2.0 * eta * rel <= 0.1 * tol || rel <= 0.01 * tol) ? 1 : 0;
-            if (state == 0 && (alpha < 0.01 || chord_it >= 2000 + 14)) state = 2;   // struggling: hand over to exact Newton
+            if (state == 0 && (alpha < 0.01 || step_kind >= 2000 + 14)) state = 2;   // struggling: hand over to exact Newton
             pcg_s[trial * 4 + 2] = fmin(1e-2, fmax(1e-9, 0.03 * rel));
         } else {
             const double rho = (prev > 0.0) ? sl / prev : 1.0;
@@ -285,28 +310,36 @@ __global__ void __launch_bounds__(256) polish_kernel(double *__restrict__ x, con
     if (threadIdx.x == 0) steplen[trial] = dmax;
 }
 
-// wbar[k] = mean over the listed trials and all bins of W[trial][k,k][t]
+// wbar[k] = mean over active trials and bins of W[trial,k,k,t], in two deterministic stages: WD_PARTS partial sums
+// per latent, added in a fixed order by the consumer.
+#define WD_PARTS 64
 __global__ void __launch_bounds__(256) wdiag_mean_kernel(const double *__restrict__ W, const int *act, int n_act, int q, int T,
-                                                         double *__restrict__ wbar) {
+                                                         double *__restrict__ wpart) {
     __shared__ double red[32];
     const int k = blockIdx.x;
     double s = 0.0;
-    const long long tot = (long long)n_act * T;
-    for (long long i = threadIdx.x; i < tot; i += blockDim.x) {
-        const int trial = act[i / T];
-        s += W[((size_t)trial * q * q + k * q + k) * T + (i % T)];
+    for (int a = blockIdx.y; a < n_act; a += WD_PARTS) {
+        const double *Wk = W + ((size_t)act[a] * q * q + k * q + k) * T;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) s += Wk[t];
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) wbar[k] = s / (double)tot;
+    if (threadIdx.x == 0) wpart[k * WD_PARTS + blockIdx.y] = s;
 }
 
 // M[k] = Kinv[k] + wbar[k] I
-__global__ void shift_diag_kernel(const double *__restrict__ Kinv, const double *__restrict__ wbar, int T, double *__restrict__ M) {
+__global__ void shift_diag_kernel(const double *__restrict__ Kinv, const double *__restrict__ wpart, double inv_count, int T,
+                                  double *__restrict__ M) {
     const int k = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= T * T) return;
     const int i = e / T, j = e - i * T;
-    M[(size_t)k * T * T + e] = Kinv[(size_t)k * T * T + e] + (i == j ? wbar[k] : 0.0);
+    double v = Kinv[(size_t)k * T * T + e];
+    if (i == j) {
+        double sacc = 0.0;
+        for (int pidx = 0; pidx < WD_PARTS; pidx++) sacc += wpart[k * WD_PARTS + pidx];
+        v += sacc * inv_count;
+    }
+    M[(size_t)k * T * T + e] = v;
 }
 
 __global__ void scatter_slots_kernel(const int *act, int n, int *map) {
@@ -483,12 +516,12 @@ int launch_eval(const double *x, const double *Kx, const double *y, const double
 template <int Q>
 int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
                       const double *C, const double *d, const double *off, const int *act, int nslots, int N, int T, double tol,
-                      double *fcur, int *conv, int *niter, double *steplen, int chord_it, cudaStream_t st, LooMap loo,
+                      double *fcur, int *conv, int *niter, double *steplen, int step_kind, cudaStream_t st, LooMap loo,
                       double *pcg_s) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, chord_it, loo, pcg_s);
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, step_kind, loo, pcg_s);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -498,11 +531,8 @@ int launch_linesearch(double *x, const double *dx, const double *Kx, const doubl
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
                         cudaStream_t st) {
     if (nslots <= 0) return PGPFA_OK;
-    const size_t smem = (size_t)PA_TR * T * sizeof(double);
-    if (smem > 48 * 1024)
-        PGPFA_CUDA_TRY(cudaFuncSetAttribute(prior_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(q, (nslots + PA_TR - 1) / PA_TR);
-    prior_apply_kernel<<<grid, 256, smem, st>>>(Kmat, v, out, act, nslots, q, T);
+    dim3 grid(q, (T + PA_TS - 1) / PA_TS, (nslots + PA_TN - 1) / PA_TN);
+    prior_apply_kernel<<<grid, 128, 0, st>>>(Kmat, v, out, act, nslots, q, T);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -521,11 +551,11 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
-                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
+                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int step_kind,
                        cudaStream_t st, const double *off, LooMap loo, double *pcg_s) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, chord_it, st, loo, pcg_s);
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, step_kind, st, loo, pcg_s);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -596,7 +626,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += align_up((size_t)R * q * q * T * 8);
     b += 2 * align_up((size_t)R * 8);
     b += 5 * align_up((size_t)R * 4) + 256;
-    b += 2 * align_up((size_t)q * T * T * 8) + 3 * align_up((size_t)q * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
+    b += 2 * align_up((size_t)q * T * T * 8) + 2 * align_up((size_t)q * 8) + align_up((size_t)q * WD_PARTS * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
     b += align_up((size_t)npairs_max * sizeof(int2));
     return b;
 }
@@ -643,7 +673,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.cnt = (int *)take(256);
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
     w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)q * T * T * 8);
-    w.wbar = (double *)take((size_t)q * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
+    w.wbar = (double *)take((size_t)q * WD_PARTS * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
     w.pws_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
     w.pws = take((size_t)w.pws_bytes);
     w.L = (double *)take((size_t)chunk * ltl * PGPFA_TILE * 8);
@@ -663,7 +693,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
     const bool dbg = getenv("PGPFA_DEBUG") != nullptr;
-    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, chord_its = 0, chord_fallback = 0, fresh_sweeps = 0, pcg_its = 0;
+    int total_factor_trials = 0, max_it_used = 0, not_converged = 0, inexact_its = 0, fallback_trials = 0, fresh_sweeps = 0, pcg_its = 0;
     const double solve_bytes = 2.0 * (double)(ltl + nb) * PGPFA_TILE * 8;
     auto read_count = [&](int &dst) -> int {
         PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -693,10 +723,11 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                 pgpfa_prof_end(h, st);
                 if (it == 0) {
                     pgpfa_prof_begin(h, PGPFA_PROF_BLOCKFACTOR, st);
-                    wdiag_mean_kernel<<<q, 256, 0, st>>>(w.W, act, n_act, q, T, w.wbar);
+                    dim3 gwd(q, WD_PARTS);
+                    wdiag_mean_kernel<<<gwd, 256, 0, st>>>(w.W, act, n_act, q, T, w.wbar);
                     PGPFA_LAUNCH_CHECK();
                     dim3 gsh((T * T + 255) / 256, q);
-                    shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, T, w.Mk);
+                    shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, 1.0 / ((double)n_act * T), T, w.Mk);
                     PGPFA_LAUNCH_CHECK();
                     PGPFA_TRY(pgpfa_spd_inverse_batched(w.Mk, q, T, w.Minv, w.plogdet, w.pinfo, w.pws, w.pws_bytes, st));
                     pgpfa_prof_end(h, st);
@@ -731,7 +762,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                 if (dbg) fprintf(stderr, "[pgpfa] outer %d done: %d trials continue\n", it, n_act);
                 act = outp;
                 act_next = (act == w.actA) ? w.actB : w.actA;
-                chord_its = it + 1;
+                inexact_its = it + 1;
             }
             // trials that struggled (state 2) or ran out of inexact-Newton iterations (state 0) go to exact Newton
             iota_kernel<<<(cn + 255) / 256, 256, 0, st>>>(act_next, cn, c0);
@@ -739,7 +770,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             compact_active_kernel<<<1, 1024, 0, st>>>(act_next, cn, w.conv, 5, act, w.cnt);
             PGPFA_LAUNCH_CHECK();
             PGPFA_TRY(read_count(n_act));
-            chord_fallback += n_act;
+            fallback_trials += n_act;
         }
         // ---- phase B: exact Newton with fresh factorisations; every factor is re-used for a few chord sweeps
         // (4 ms each for 1024 trials) before anything is factorised again
@@ -839,8 +870,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         stats_out[1] = max_it_used;
         stats_out[2] = not_converged;
         stats_out[3] = chunk;
-        stats_out[4] = chord_its;
-        stats_out[5] = chord_fallback;
+        stats_out[4] = inexact_its;
+        stats_out[5] = fallback_trials;
         stats_out[6] = (chunk >= R) ? 1 : 0;     // the workspace now holds every trial's factor at its mode
         stats_out[7] = fresh_sweeps + 1000 * pcg_its;
     }

@@ -241,62 +241,75 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
 }
 
 // C = A * B for a batch of row-major n x n matrices on the FP64 tensor pipe (DMMA.8x8x4): CTA = 64x64 tile of C,
-// 4 warps as 2x2 of 32x32, k in chunks of 16 staged through padded shared memory (conflict-free fragment loads:
-// A stride 20 and B stride 68 doubles put the 16 lanes of a half-warp on 16 distinct 8-byte banks).
+// 4 warps as 2x2 of 32x32, k in chunks of 16 through double-buffered padded shared memory (conflict-free fragment
+// loads: A stride 20 and B stride 68 doubles put the 16 lanes of a half-warp on 16 distinct 8-byte banks); the next
+// chunk's global loads are in flight while the current one is multiplied.
 __global__ void __launch_bounds__(128) small_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                          double *__restrict__ Cm, int n) {
-    __shared__ double As[64][20], Bs[16][68];
+    __shared__ double As[2][64][20], Bs[2][16][68];
     const int b = blockIdx.z;
     const double *Ab = A + (size_t)b * n * n, *Bb = B + (size_t)b * n * n;
     double *Cb = Cm + (size_t)b * n * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     const int fr = lane >> 2, fk = lane & 3;
+    const int ar = tid >> 4, ac = tid & 15;        // A: rows ar + 8 j, column ac of the chunk
+    const int bk = tid >> 6, bc = tid & 63;        // B: rows bk + 2 j, column bc of the chunk
+    double ra[8], rb[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const int r = r0 + ar + 8 * jj, kk = k0 + bk + 2 * jj;
+            ra[jj] = (r < n && k0 + ac < n) ? Ab[(size_t)r * n + k0 + ac] : 0.0;
+            rb[jj] = (kk < n && c0 + bc < n) ? Bb[(size_t)kk * n + c0 + bc] : 0.0;
+        }
+    };
     double acc[4][4][2] = {};
-    for (int k0 = 0; k0 < n; k0 += 16) {
-        for (int i = tid; i < 64 * 16; i += 128) {
-            const int rr = i >> 4, kk = i & 15;
-            As[rr][kk] = (r0 + rr < n && k0 + kk < n) ? Ab[(size_t)(r0 + rr) * n + k0 + kk] : 0.0;
-            const int k2 = i >> 6, cc = i & 63;
-            Bs[k2][cc] = (k0 + k2 < n && c0 + cc < n) ? Bb[(size_t)(k0 + k2) * n + c0 + cc] : 0.0;
+    fetch(0);
+    int buf = 0;
+    for (int k0 = 0; k0 < n; k0 += 16, buf ^= 1) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            As[buf][ar + 8 * jj][ac] = ra[jj];
+            Bs[buf][bk + 2 * jj][bc] = rb[jj];
         }
         __syncthreads();
+        if (k0 + 16 < n) fetch(k0 + 16);
 #pragma unroll
         for (int k4 = 0; k4 < 16; k4 += 4) {
             double a[4], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[wm * 32 + i * 8 + fr][k4 + fk];
+            for (int i = 0; i < 4; i++) a[i] = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
 #pragma unroll
-            for (int j = 0; j < 4; j++) bb[j] = Bs[k4 + fk][wn * 32 + j * 8 + fr];
+            for (int jj = 0; jj < 4; jj++) bb[jj] = Bs[buf][k4 + fk][wn * 32 + jj * 8 + fr];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+                for (int jj = 0; jj < 4; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], bb[jj]);
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int jj = 0; jj < 4; jj++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int r = r0 + wm * 32 + i * 8 + fr, c = c0 + wn * 32 + j * 8 + 2 * fk + e;
-                if (r < n && c < n) Cb[(size_t)r * n + c] = acc[i][j][e];
+                const int r = r0 + wm * 32 + i * 8 + fr, c = c0 + wn * 32 + jj * 8 + 2 * fk + e;
+                if (r < n && c < n) Cb[(size_t)r * n + c] = acc[i][jj][e];
             }
 }
 
-// cost / gradient of the timescale objective from Kinv, logdet, dK, G = Kinv dK Kinv and PautoSum
-__global__ void __launch_bounds__(256) tau_reduce_kernel(const double *__restrict__ p, const double *__restrict__ Kinv,
-                                                         const double *__restrict__ dK, const double *__restrict__ G,
-                                                         const double *__restrict__ P, const double *__restrict__ logdet,
-                                                         double R, int T, double pw, const double *__restrict__ tau_old,
-                                                         double bs, double *__restrict__ cost, double *__restrict__ grad) {
+// cost / gradient of the timescale objective from Kinv, logdet, dK, G = Kinv dK Kinv and PautoSum.
+// Stage 1: TAU_PARTS CTAs per slot reduce slices of the three traces; stage 2 adds them in a fixed order.
+#define TAU_PARTS 8
+__global__ void __launch_bounds__(256) tau_trace_kernel(const double *__restrict__ Kinv, const double *__restrict__ dK,
+                                                        const double *__restrict__ G, const double *__restrict__ P, int T,
+                                                        double *__restrict__ part) {
     __shared__ double red[32];
     const int k = blockIdx.x;
     const size_t off = (size_t)k * T * T;
     double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < T * T; e += blockDim.x * TAU_PARTS) {
         const double ki = Kinv[off + e], pp = P[off + e];
         t1 += ki * pp;
         t2 += ki * dK[off + e];
@@ -306,18 +319,33 @@ __global__ void __launch_bounds__(256) tau_reduce_kernel(const double *__restric
     t2 = block_sum(t2, red);
     t3 = block_sum(t3, red);
     if (threadIdx.x == 0) {
-        double c = 0.5 * R * logdet[k] + 0.5 * t1;
-        const double dE = -0.5 * R * t2 + 0.5 * t3;
-        double g = -dE * exp(p[k]);
-        if (pw > 0.0) {
-            const double tau = bs / 1000.0 * sqrt(1.0 / exp(p[k]));
-            const double dt = tau - tau_old[k];
-            c += 0.5 * dt * dt * pw;
-            g += dt * pw;      // as written in funs/learning.py:734,769 (no chain-rule factor)
-        }
-        cost[k] = c;
-        grad[k] = g;
+        double *o = part + ((size_t)k * TAU_PARTS + blockIdx.y) * 3;
+        o[0] = t1; o[1] = t2; o[2] = t3;
     }
+}
+
+__global__ void tau_reduce_kernel(const double *__restrict__ p, const double *__restrict__ part,
+                                  const double *__restrict__ logdet, int nslots, double R, double pw,
+                                  const double *__restrict__ tau_old, double bs, double *__restrict__ cost,
+                                  double *__restrict__ grad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int i = 0; i < TAU_PARTS; i++) {
+        const double *o = part + ((size_t)k * TAU_PARTS + i) * 3;
+        t1 += o[0]; t2 += o[1]; t3 += o[2];
+    }
+    double c = 0.5 * R * logdet[k] + 0.5 * t1;
+    const double dE = -0.5 * R * t2 + 0.5 * t3;
+    double g = -dE * exp(p[k]);
+    if (pw > 0.0) {
+        const double tau = bs / 1000.0 * sqrt(1.0 / exp(p[k]));
+        const double dt = tau - tau_old[k];
+        c += 0.5 * dt * dt * pw;
+        g += dt * pw;      // as written in funs/learning.py:734,769 (no chain-rule factor)
+    }
+    cost[k] = c;
+    grad[k] = g;
 }
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -389,7 +417,8 @@ extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double p
 extern "C" long long pgpfa_tau_eval_workspace_bytes(int q, int T) {
     if (q <= 0 || T <= 0) return -1;
     const size_t mat = align_up((size_t)q * T * T * 8);
-    return (long long)(5 * mat + align_up((size_t)q * 8) + align_up((size_t)q * 4)) + pgpfa_spd_inverse_workspace_bytes(q, T) + 1024;
+    return (long long)(5 * mat + align_up((size_t)q * 8) + align_up((size_t)q * 4) + align_up((size_t)q * TAU_PARTS * 24)) +
+           pgpfa_spd_inverse_workspace_bytes(q, T) + 1024;
 }
 
 extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTrials, int q, int T, double eps,
@@ -407,6 +436,7 @@ extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTri
     double *G = (double *)w; w += mat;
     double *logdet = (double *)w; w += align_up((size_t)q * 8);
     int *info = (int *)w; w += align_up((size_t)q * 4);
+    double *part = (double *)w; w += align_up((size_t)q * TAU_PARTS * 24);
     const long long inv_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
     PGPFA_TRY(pgpfa_make_K_gamma(p, q, T, eps, K, dK, st));
     PGPFA_TRY(pgpfa_spd_inverse_batched(K, q, T, Kinv, logdet, info, w, inv_bytes, st));
@@ -415,7 +445,10 @@ extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTri
     PGPFA_LAUNCH_CHECK();
     small_gemm_kernel<<<grid, 128, 0, st>>>(M1, Kinv, G, T);
     PGPFA_LAUNCH_CHECK();
-    tau_reduce_kernel<<<q, 256, 0, st>>>(p, Kinv, dK, G, Psum, logdet, numTrials, T, prior_w, tau_old, bs, cost, grad);
+    dim3 gtr(q, TAU_PARTS);
+    tau_trace_kernel<<<gtr, 256, 0, st>>>(Kinv, dK, G, Psum, T, part);
+    PGPFA_LAUNCH_CHECK();
+    tau_reduce_kernel<<<(q + 127) / 128, 128, 0, st>>>(p, part, logdet, q, numTrials, prior_w, tau_old, bs, cost, grad);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }

@@ -73,7 +73,7 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
                          cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo());
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
-                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int chord_it,
+                       int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int step_kind,
                        cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo(), double *pcg_s = nullptr);
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);

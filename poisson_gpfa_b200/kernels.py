@@ -34,10 +34,10 @@ def sample_dataset(C, d, tau, R, T, binSize, seed, epsNoise=0.001):
     N = C.shape[0]
     K = make_K(tau, T, binSize, epsNoise)
     L, D, _, info = potrf_dense(K, want_zt=False)
-    Lt = tiles_to_dense(L, T).transpose(1, 2).contiguous()          # prior_apply multiplies by the transpose
+    Ld = tiles_to_dense(L, T)
     z = empty(R, q, T)
     call("pgpfa_sample_normal", ptr(z), z.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, stream())
-    X = prior_apply(Lt, z)                                          # x_k = chol(K_k) z_k
+    X = prior_apply(Ld, z)                                          # x_k = chol(K_k) z_k
     Y = empty(R, N, T)
     call("pgpfa_sample_poisson", ptr(X), ptr(C), ptr(d), R, q, N, T, (int(seed) * 0x9E3779B97F4A7C15 + 1) & 0xFFFFFFFFFFFFFFFF,
          ptr(Y), stream())

@@ -71,6 +71,16 @@ def test_kinv_of_prior():
     assert rel(logdet, np.linalg.slogdet(K)[1]) <= 1e-12
 
 
+@pytest.mark.parametrize("q,T,R", [(1, 5, 1), (3, 70, 37), (8, 200, 70), (2, 129, 33)])
+def test_prior_apply_is_a_batched_matrix_product(q, T, R):
+    """out[r,k,:] = Kmat[k] @ v[r,k,:] for general (also non-symmetric) matrices, ragged tile edges included."""
+    from poisson_gpfa_b200 import kernels as kn
+    rng = np.random.RandomState(q * 1000 + T)
+    Kmat, v = rng.randn(q, T, T), rng.randn(R, q, T)
+    out = kn.prior_apply(dev(Kmat), dev(v))
+    assert rel(out, np.einsum('kst,rkt->rks', Kmat, v)) <= 1e-13
+
+
 @pytest.mark.parametrize("n,b", [(100, 3), (192, 2), (450, 2), (1600, 2)])
 def test_factor_solve_invert(n, b):
     from poisson_gpfa_b200 import kernels as kn
