@@ -20,6 +20,18 @@ from .dist import Reducer
 EPS_NOISE = 0.001   # funs/util.py:599, funs/learning.py:286
 
 
+_side_streams = {}
+
+
+def _side_stream():
+    """One high-priority stream per device for the whole process (mini-batch EM creates many DeviceTrials; a stream
+    per object would leave a trail of per-stream allocator pools)."""
+    dev = torch.cuda.current_device()
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(priority=-1)
+    return _side_streams[dev]
+
+
 class DeviceParams:
     """C (N,q), d (N), tau (q, seconds) on the device plus the derived prior blocks."""
 
@@ -87,7 +99,6 @@ class DeviceTrials:
         self._lap_ws = None
         self._cd_ws = None
         self._tau_ws = None
-        self._side = None
 
     def _means_stream(self):
         """High-priority stream ordered after the point of the last Laplace solve where the posterior means and
@@ -95,10 +106,9 @@ class DeviceTrials:
         M-step run there, underneath the selected-inverse kernel that is still producing post_vsmGP."""
         if os.environ.get("PGPFA_SIDE_STREAM", "1") == "0":      # debugging switch: everything on the caller's stream
             return None
-        if self._side is None:
-            self._side = torch.cuda.Stream(priority=-1)
-        call("pgpfa_stream_wait_means", handle(), self._side.cuda_stream)
-        return self._side
+        side = _side_stream()
+        call("pgpfa_stream_wait_means", handle(), side.cuda_stream)
+        return side
 
     # ------------------------------------------------------------------ E-step
     def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True):
