@@ -247,3 +247,35 @@ def test_stevenson_style_loader_bins_like_numpy_histogram():
     np.random.seed(0)
     fit = engine.PPGPFAfit(experiment=ds, xdim=2, inferenceMethod='laplace', EMmode='Batch', maxEMiter=2, quiet=True)
     assert len(fit.posteriorLikelihood) == 2 and np.all(np.isfinite(fit.optimParams['C']))
+
+
+def test_side_stream_mstep_is_bit_identical_to_single_stream(monkeypatch):
+    """The C,d M-step runs on a second stream underneath the selected inverse (pgpfa_stream_wait_means); it must give
+    exactly what the single-stream ordering gives (every kernel is deterministic), over several EM iterations and at a
+    batch size that takes the split-stream factorisation path."""
+    from poisson_gpfa_b200 import core, util
+    ex = util.simulate(11, 3, 15, 70, 40)
+    Y = np.stack([np.asarray(t['Y'], dtype=np.float64) for t in ex.data])
+    rng = np.random.RandomState(3)
+    ip = {'C': 0.3 * rng.randn(15, 3), 'd': np.log(Y.mean(axis=(0, 2)) + 0.1), 'tau': np.array([0.1, 0.15, 0.2])}
+
+    def run(flag):
+        monkeypatch.setenv("PGPFA_SIDE_STREAM", flag)
+        trials = core.DeviceTrials(Y, ex.binSize)
+        params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], ex.T, ex.binSize)
+        x0, out = None, []
+        for _ in range(3):
+            est = trials.estep_laplace(params, x0=x0)
+            assert (est.side is None) == (flag == "0")
+            lik = trials.post_lik(est)
+            C, d, cost, _, _ = trials.mstep_cd(params, est)
+            tau, _ = trials.mstep_tau(params, trials.pautosum(est))
+            params = core.DeviceParams(C, d, tau, ex.T, ex.binSize)
+            x0 = est.x
+            out.append((lik, cost, C.cpu().numpy(), d.cpu().numpy(), np.asarray(tau), est.vsmGP.cpu().numpy()))
+        return out
+
+    a, b = run("1"), run("0")
+    for (la, ca, Ca, da, ta, va), (lb, cb, Cb, db, tb, vb) in zip(a, b):
+        assert la == lb and ca == cb
+        assert np.array_equal(Ca, Cb) and np.array_equal(da, db) and np.array_equal(ta, tb) and np.array_equal(va, vb)
