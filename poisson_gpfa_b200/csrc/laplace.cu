@@ -364,6 +364,15 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
     const double *vp = vsmGP + (size_t)k * T * T + e;
     const double *mp = m + (size_t)k * T;
     int r = 0;
+    // eight trials' loads in flight per thread; the additions keep the even/odd order of the two-term loop below
+    for (; r + 7 < R; r += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            v[u] = vp[(size_t)(r + u) * strideV] + mp[(size_t)(r + u) * strideM + s] * mp[(size_t)(r + u) * strideM + t];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) { a0 += v[u]; a1 += v[u + 1]; }
+    }
     for (; r + 1 < R; r += 2) {
         a0 += vp[(size_t)r * strideV] + mp[(size_t)r * strideM + s] * mp[(size_t)r * strideM + t];
         a1 += vp[(size_t)(r + 1) * strideV] + mp[(size_t)(r + 1) * strideM + s] * mp[(size_t)(r + 1) * strideM + t];
