@@ -108,7 +108,7 @@ long long pgpfa_laplace_workspace_bytes(int R, int q, int T, int chunk);
  * flags = 0 runs for every trial.  Same fixed point either way.
  * vsm / vsmGP / cov_dense may be NULL (skipped).  stats_out[8] = {trial-factorisations, max exact-Newton
  * iterations, trials not converged, chunk size, inexact-Newton iterations, trials that fell back to exact Newton,
- * whole batch in one chunk (1/0), chord sweeps + 1000 * CG iterations}. */
+ * rank r of the prior factor if the low-rank posterior pass ran (else 0), chord sweeps + 1000 * CG iterations}. */
 int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
                         double *x, int R, int q, int N, int T, double tol, int max_newton, int flags,
                         double *f_out, double *vsm, double *vsmGP, double *cov_dense, int *niter, int *info,
@@ -118,6 +118,22 @@ int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const double *C, cons
  * be running on the solve's own stream.  Lets the C,d M-step (which needs only x and vsm, funs/learning.py:28-91)
  * run on a second stream underneath the tensor-bound selected inverse.  No-op before the first solve. */
 int pgpfa_stream_wait_means(pgpfa_handle_t h, cudaStream_t waiting_stream);
+
+/* Low-rank factor of the smooth part of the GP prior: K_k - eps I = F_k F_k^T by pivoted Cholesky, stopped when the
+ * largest residual diagonal entry is <= delta (K from pgpfa_make_K with the same eps, funs/util.py:599-619).
+ * F (q,T,T) row-major [k][t][a], Ft (q,T,T) = [k][a][t]; columns / rows >= rank[k] are zero.  rank: q ints (device). */
+int pgpfa_prior_lowrank(const double *K, int q, int T, double eps, double delta, double *F, double *Ft, int *rank,
+                        cudaStream_t stream);
+/* pgpfa_laplace_solve with the posterior pass done through that factor: with Y = P F L_b^-T, P_t = (I + eps W_t)^-1 and
+ * L_b L_b^T = I + F^T (W P) F (r x r, r = sum of the ranks), Sigma = eps P + Y Y^T exactly, so post_vsm / post_vsmGP
+ * and the polishing Newton step need no qT x qT factorisation.  Same outputs as pgpfa_laplace_solve to the
+ * truncation level delta (no dense covariance output).  rank_host: q ints on the HOST.  Falls back to the dense tiled
+ * path when the scratch for rank r does not fit into the workspace's factor area.  stats_out[6] = r when it ran. */
+int pgpfa_laplace_solve_lowrank(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
+                                const double *F, const double *Ft, const int *rank_host, double eps, double *x, int R,
+                                int q, int N, int T, double tol, int max_newton, int flags, double *f_out, double *vsm,
+                                double *vsmGP, int *niter, int *info, void *workspace, long long ws_bytes,
+                                int *stats_out, cudaStream_t stream);
 
 /* Leave-one-neuron-out prediction, funs/engine.py:599-644: problem p = (trial ymap[p], left-out neuron excl[p]);
  * the posterior mode is found without that neuron (x: P x q x T, in = start, out = mode) and its rate predicted:

@@ -24,6 +24,9 @@ SIGNATURES = {
     "pgpfa_last_cuda_error": (ctypes.c_char_p, []),
     "pgpfa_launch_count": (c_ll, []),
     "pgpfa_stream_wait_means": (c_int, [c_void_p, c_void_p]),
+    "pgpfa_prior_lowrank": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P, P, P]),
+    "pgpfa_laplace_solve_lowrank": (c_int, [c_void_p, P, P, P, P, P, P, P, c_dbl, P, c_int, c_int, c_int, c_int, c_dbl, c_int,
+                                            c_int, P, P, P, P, P, P, c_ll, P, P]),
     "pgpfa_set_profiling": (c_int, [c_void_p, c_int]),
     "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
     "pgpfa_map": (c_int, [c_int, c_ll, P, P, c_dbl, P, P]),

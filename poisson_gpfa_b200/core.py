@@ -18,6 +18,7 @@ from ._lib import call, empty, handle, ptr, stream
 from .dist import Reducer
 
 EPS_NOISE = 0.001   # funs/util.py:599, funs/learning.py:286
+LOWRANK_DELTA = 1e-14   # residual of the pivoted Cholesky of the smooth part of K (relative to its unit diagonal)
 
 
 _side_streams = {}
@@ -41,6 +42,7 @@ class DeviceParams:
         self.tau = _lib.dev_f64(np.ravel(tau) if not isinstance(tau, torch.Tensor) else tau.reshape(-1))
         self.T, self.binSize = int(T), float(binSize)
         self._K = self._Kinv = self._logdetK = None
+        self._lowrank = False
 
     @property
     def q(self):
@@ -61,6 +63,19 @@ class DeviceParams:
             if int(info.abs().max()) != 0:
                 raise FloatingPointError("GP prior covariance K is not positive definite (tau=%s)" % self.tau.tolist())
         return self._Kinv
+
+    @property
+    def lowrank(self):
+        """(F, Ft, ranks, eps) with K_k - eps I = F_k F_k^T (pivoted Cholesky, residual <= 1e-14), or None when the
+        prior's numerical rank is not small (sum of ranks > qT/2: short timescales) and the dense path is the cheaper
+        one.  PGPFA_LOWRANK=0 disables it."""
+        if self._lowrank is False:
+            self._lowrank = None
+            if os.environ.get("PGPFA_LOWRANK", "1") != "0":
+                F, Ft, ranks = kn.prior_lowrank(self.K, EPS_NOISE, LOWRANK_DELTA)
+                if 0 < sum(ranks) <= (self.q * self.T) // 2:
+                    self._lowrank = (F, Ft, ranks, EPS_NOISE)
+        return self._lowrank
 
     def to_numpy_dict(self):
         return {'C': self.C.cpu().numpy(), 'd': self.d.cpu().numpy(), 'tau': self.tau.cpu().numpy()}
@@ -121,7 +136,8 @@ class DeviceTrials:
             nbytes = full if full <= budget else max(budget, _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, 1))
             self._lap_ws = ((R, q, T), _lib.workspace(nbytes))
         res = kn.laplace_solve(self.y, params.C, params.d, params.Kinv, x0=x0, tol=tol, max_newton=max_newton,
-                               want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton)
+                               want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton,
+                               lowrank=params.lowrank)
         est = EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
         est.side = self._means_stream()
         with est.means_stream():

@@ -594,6 +594,14 @@ int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, 
     return PGPFA_OK;
 }
 
+int pgpfa_i_polish(double *x, const double *dx, const int *act, int n, double max_rel, double *steplen, int nslots,
+                   cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    polish_kernel<<<nslots, 256, 0, st>>>(x, dx, act, n, max_rel, steplen);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all) {
     const int n = q * T, nb = pgpfa_nb(n);
     std::set<std::pair<int, int>> s;
@@ -622,6 +630,7 @@ struct LapWs {
     void *pws;
     long long pws_bytes;
     int2 *pairs;
+    void *lr_tables;
     double *L, *Dinv, *ZT;
     float *L32, *D32;
     int chunk;
@@ -636,7 +645,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += 2 * align_up((size_t)R * 8);
     b += 5 * align_up((size_t)R * 4) + 256;
     b += 2 * align_up((size_t)q * T * T * 8) + 2 * align_up((size_t)q * 8) + align_up((size_t)q * WD_PARTS * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
-    b += align_up((size_t)npairs_max * sizeof(int2));
+    b += align_up((size_t)npairs_max * sizeof(int2)) + align_up(PGPFA_LOWRANK_TABLE_BYTES);
     return b;
 }
 size_t lap_per_trial_bytes(int q, int T) {
@@ -656,7 +665,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                               const double *Kinv, double *x, int R, int q, int N, int T, double tol,
                               int max_newton, int flags, double *f_out, double *vsm, double *vsmGP,
                               double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
-                              int *stats_out, cudaStream_t st, LooMap loo, bool posterior_pass) {
+                              int *stats_out, cudaStream_t st, LooMap loo, bool posterior_pass,
+                              const PgpfaLowRank *lr = nullptr) {
     if (!h || !y || !C || !d || !Kinv || !x || !f_out || !niter || !info || !workspace) return PGPFA_ERR_ARG;
     if (R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0 || max_newton <= 0) return PGPFA_ERR_ARG;
     const int n = q * T, nb = pgpfa_nb(n);
@@ -681,6 +691,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.actC = (int *)take((size_t)R * 4); w.lslot = (int *)take((size_t)R * 4);
     w.cnt = (int *)take(256);
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
+    w.lr_tables = take(PGPFA_LOWRANK_TABLE_BYTES);
     w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)q * T * T * 8);
     w.wbar = (double *)take((size_t)q * WD_PARTS * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
     w.pws_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
@@ -695,6 +706,11 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(w.conv, 0, (size_t)R * 4, st));
+    // low-rank posterior pass (lowrank.cu) when a prior factor is given, no dense covariance is wanted and its scratch
+    // fits into the factor area of the workspace; otherwise the dense tiled path
+    bool use_lr = lr && lr->r > 0 && posterior_pass && !cov_dense &&
+                  pgpfa_i_lowrank_bytes_per_slot(q, T, lr->r) <= per;
+    if (use_lr) PGPFA_TRY(pgpfa_i_lowrank_prepare(*lr, q, T, w.lr_tables, st));
     std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, cov_dense != nullptr);
     PGPFA_CUDA_TRY(cudaMemcpyAsync(w.pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     PGPFA_CUDA_TRY(cudaStreamSynchronize(st));   // pairs is a host temporary
@@ -847,7 +863,11 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, w.actA, cn, q, T, st));
         PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, w.actA, cn, q, N, T, f_out, w.g, w.W, st, nullptr, loo));
         pgpfa_prof_end(h, st);
-        if (posterior_pass) {
+        if (posterior_pass && use_lr) {
+            PGPFA_TRY(pgpfa_i_lowrank_posterior(h, *lr, w.W, w.g, x, w.dx, w.actA, cn, q, T, tol, w.steplen, vsm, vsmGP,
+                                                w.L, w.lr_tables, st));
+            total_factor_trials += cn;
+        } else if (posterior_pass) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h, w.L32, w.D32));
             pgpfa_prof_end(h, st);
@@ -881,7 +901,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         stats_out[3] = chunk;
         stats_out[4] = inexact_its;
         stats_out[5] = fallback_trials;
-        stats_out[6] = (chunk >= R) ? 1 : 0;     // the workspace now holds every trial's factor at its mode
+        stats_out[6] = use_lr ? lr->r : 0;       // rank of the prior factor when the low-rank posterior pass ran
         stats_out[7] = fresh_sweeps + 1000 * pcg_its;
     }
     return not_converged ? PGPFA_ERR_NOT_CONVERGED : PGPFA_OK;
@@ -896,6 +916,27 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
     loo.ymap = nullptr; loo.excl = nullptr;
     return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, flags, f_out, vsm, vsmGP, cov_dense,
                               niter, info, workspace, ws_bytes, stats_out, st, loo, true);
+}
+
+extern "C" int pgpfa_laplace_solve_lowrank(pgpfa_handle_t h, const double *y, const double *C, const double *d,
+                                           const double *Kinv, const double *F, const double *Ft, const int *rank_host,
+                                           double eps, double *x, int R, int q, int N, int T, double tol, int max_newton,
+                                           int flags, double *f_out, double *vsm, double *vsmGP, int *niter, int *info,
+                                           void *workspace, long long ws_bytes, int *stats_out, cudaStream_t st) {
+    if (!F || !Ft || !rank_host || q <= 0 || q > PGPFA_QMAX || !(eps > 0.0)) return PGPFA_ERR_ARG;
+    PgpfaLowRank lr;
+    lr.F = F; lr.Ft = Ft; lr.eps = eps; lr.r = 0;
+    for (int k = 0; k < q; k++) {
+        if (rank_host[k] < 0 || rank_host[k] > T) return PGPFA_ERR_ARG;
+        lr.rank[k] = rank_host[k];
+        lr.off[k] = lr.r;
+        lr.r += rank_host[k];
+    }
+    lr.off[q] = lr.r;
+    LooMap loo;
+    loo.ymap = nullptr; loo.excl = nullptr;
+    return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, flags, f_out, vsm, vsmGP, nullptr,
+                              niter, info, workspace, ws_bytes, stats_out, st, loo, true, &lr);
 }
 
 // y_pred[p][t] = exp(c_n . x_p[:,t] + d_n) for the left-out neuron n = excl[p]; err[p] = sum_t (y - y_pred)^2

@@ -1,0 +1,599 @@
+// Posterior covariance slices through the low-rank structure of the GP prior.
+//
+// The reference builds K_k = (1-eps) SE(tau_k) + eps I per latent (funs/util.py:599-619) and inverts the dense
+// qT x qT Hessian H = blkdiag(K_k^-1) + D, D = the per-bin q x q blocks W_t (funs/inference.py:50-65, :164-172).
+// The squared-exponential part has a rapidly decaying spectrum: a pivoted Cholesky K_k - eps I = F_k F_k^T stops at
+// rank r_k << T with residual below 1e-14.  With F = blkdiag(F_k) (qT x r, r = sum r_k) and the per-bin matrices
+// P_t = (I + eps W_t)^-1, Dt_t = W_t P_t, the Woodbury identity gives EXACTLY (up to that residual)
+//     Sigma = H^-1 = eps P + Y Y^T,   Y = P F L_b^-T,   L_b L_b^T = I_r + F^T Dt F        (r x r instead of qT x qT)
+// so the slices the EM needs are
+//     post_vsm[t]    = eps P_t + Y_(.,t) Y_(.,t)^T            (q x q per bin)
+//     post_vsmGP[k]  = eps diag(P_t[k,k]) + Y_k Y_k^T         (T x T per latent)
+// and the polishing Newton step is -Sigma g.  Neither K^-1 nor any qT x qT factorisation appears; cond(I + F^T Dt F)
+// is ~1e2 where cond(H) ~ 1e3-1e5.  Work per trial at the headline shape (q=8, T=200, r ~ 220-380): ~0.15-0.3 GFLOP
+// instead of 3.2 GFLOP.  The dense tiled path stays for priors whose numerical rank is not small (short timescales)
+// and for the dense covariance output.
+//
+// All GEMM-shaped steps (F^T Dt F, F L_b^-T, Y_k Y_k^T) run through one batched NT kernel on the FP64 tensor pipe
+// (DMMA.8x8x4); the r x r factorisation and triangular inverse are the tile kernels of factor.cu.
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+#include "pgpfa_internal.h"
+
+using namespace pgpfa;
+
+namespace {
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------
+// pivoted Cholesky of S_k = K_k - eps I, one CTA per latent:  F_k (T x T row-major [t][a], columns >= rank zero),
+// Ft_k = F_k^T ([a][t]), rank[k].  Stops when the largest residual diagonal entry is <= delta.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pivchol_kernel(const double *__restrict__ K, int T, double eps, double delta,
+                                                      double *__restrict__ F, double *__restrict__ Ft, int *__restrict__ rank) {
+    extern __shared__ double sm[];
+    double *dres = sm, *fj = sm + T;
+    __shared__ double redv[8];
+    __shared__ int redi[8];
+    __shared__ double s_dmax;
+    __shared__ int s_piv;
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *Kk = K + (size_t)k * T * T;
+    double *Fk = F + (size_t)k * T * T, *Ftk = Ft + (size_t)k * T * T;
+    for (int t = tid; t < T; t += blockDim.x) dres[t] = Kk[(size_t)t * T + t] - eps;
+    __syncthreads();
+    int r = 0;
+    for (; r < T; r++) {
+        double best = -1.0;
+        int bi = T;
+        for (int t = tid; t < T; t += blockDim.x)
+            if (dres[t] > best) { best = dres[t]; bi = t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
+        }
+        if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = redv[0];
+            int i = redi[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+                if (redv[w] > b || (redv[w] == b && redi[w] < i)) { b = redv[w]; i = redi[w]; }
+            s_dmax = b;
+            s_piv = i;
+        }
+        __syncthreads();
+        if (!(s_dmax > delta)) break;
+        const int j = s_piv;
+        for (int a = tid; a < r; a += blockDim.x) fj[a] = Fk[(size_t)j * T + a];
+        __syncthreads();
+        const double inv = 1.0 / sqrt(s_dmax);
+        for (int t = tid; t < T; t += blockDim.x) {
+            double s = Kk[(size_t)t * T + j] - (t == j ? eps : 0.0);
+            const double *ft = Fk + (size_t)t * T;
+            for (int a = 0; a < r; a++) s -= ft[a] * fj[a];
+            const double c = s * inv;
+            Fk[(size_t)t * T + r] = c;
+            Ftk[(size_t)r * T + t] = c;
+            if (t == j) dres[t] = -1.0;                       // pivoted: never selected again
+            else if (dres[t] >= 0.0) dres[t] = fmax(dres[t] - c * c, 0.0);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) rank[k] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per (slot, bin): P = (I + eps W_t)^-1 and Dt = W_t P (both symmetric), layout (slot, q*q, T) like W
+// ---------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) lr_bins_kernel(const double *__restrict__ W, const int *__restrict__ act, int T,
+                                                      double eps, double *__restrict__ Pm, double *__restrict__ Dm) {
+    const int slot = blockIdx.y;
+    const int trial = act ? act[slot] : slot;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double *Wt = W + (size_t)trial * Q * Q * T + t;
+    double w[Q * (Q + 1) / 2], a[Q * (Q + 1) / 2];           // packed lower: (i,j) -> i(i+1)/2 + j
+#pragma unroll
+    for (int i = 0; i < Q; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            const double v = Wt[(size_t)(i * Q + j) * T];
+            w[i * (i + 1) / 2 + j] = v;
+            a[i * (i + 1) / 2 + j] = eps * v + (i == j ? 1.0 : 0.0);
+        }
+    // Cholesky a = L L^T in place
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        double dj = a[j * (j + 1) / 2 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) dj -= a[j * (j + 1) / 2 + k] * a[j * (j + 1) / 2 + k];
+        const double ljj = sqrt(dj), inv = 1.0 / ljj;
+        a[j * (j + 1) / 2 + j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < Q; i++) {
+            double s = a[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= a[i * (i + 1) / 2 + k] * a[j * (j + 1) / 2 + k];
+            a[i * (i + 1) / 2 + j] = s * inv;
+        }
+    }
+    // a <- L^-1 in place (lower), column by column
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        a[j * (j + 1) / 2 + j] = 1.0 / a[j * (j + 1) / 2 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+#pragma unroll
+        for (int i = j + 1; i < Q; i++) {
+            // X(i,j) = -X(i,i) * sum_{k=j}^{i-1} L(i,k) X(k,j); rows are finished in increasing i, and row i's
+            // off-diagonal entries still hold L(i,k) for k > j while X(i,k') for k' < j is already final
+            double s = 0.0;
+#pragma unroll
+            for (int k = j; k < i; k++) {
+                const double lik = (k == j) ? a[i * (i + 1) / 2 + j] : a[i * (i + 1) / 2 + k];
+                const double xkj = (k == j) ? a[j * (j + 1) / 2 + j] : a[k * (k + 1) / 2 + j];
+                s += lik * xkj;
+            }
+            a[i * (i + 1) / 2 + j] = -a[i * (i + 1) / 2 + i] * s;
+        }
+    }
+    // P = X^T X (symmetric), Dt = W P
+    double p[Q * (Q + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < Q; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = i; k < Q; k++) s += a[k * (k + 1) / 2 + i] * a[k * (k + 1) / 2 + j];
+            p[i * (i + 1) / 2 + j] = s;
+        }
+    double *Po = Pm + (size_t)slot * Q * Q * T + t, *Do = Dm + (size_t)slot * Q * Q * T + t;
+#pragma unroll
+    for (int i = 0; i < Q; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                const double wik = (k <= i) ? w[i * (i + 1) / 2 + k] : w[k * (k + 1) / 2 + i];
+                const double pkj = (k >= j) ? p[k * (k + 1) / 2 + j] : p[j * (j + 1) / 2 + k];
+                s += wik * pkj;
+            }
+            const double pv = p[i * (i + 1) / 2 + j];
+            Po[(size_t)(i * Q + j) * T] = pv;
+            Po[(size_t)(j * Q + i) * T] = pv;
+            Do[(size_t)(i * Q + j) * T] = s;
+            Do[(size_t)(j * Q + i) * T] = s;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched C = A B^T on the FP64 tensor pipe.  A (M x K) and B (N x K) row-major along K.  One launch covers a
+// table of problems (ragged blocks) times a batch.  CTA = 64 x 64 tile, 4 warps as 2 x 2 of 32 x 32; K in chunks of
+// 16 through double-buffered padded shared memory with register prefetch (as prior_apply_kernel / small_gemm_kernel).
+// ---------------------------------------------------------------------------------------------
+enum { GEMM_ADD_IDENTITY = 1, GEMM_SYMMETRIC = 2, GEMM_LOWER_ONLY = 4 };
+struct GemmProb {
+    long long a_off, b_off, c_off, s_off, d_off;   // element offsets into the batch's A, B, C, scale, dadd
+    int M, N, K, flags;
+};
+struct GemmArgs {
+    const double *A, *B;
+    double *C;
+    const double *scale;      // optional: B[n][k] is multiplied by scale[k]
+    const double *dadd;       // optional: C[m][m] += dadd_alpha * dadd[m]
+    long long strideA, strideB, strideC, strideS, strideD;
+    int lda, ldb, ldc;
+    const int *cmap;          // optional: C (and nothing else) is indexed by cmap[batch] instead of batch
+    const GemmProb *probs;
+    double dadd_alpha;
+};
+
+__global__ void __launch_bounds__(128) gemm_nt_kernel(GemmArgs g) {
+    __shared__ double As[2][64][20], Bs[2][64][20];
+    const GemmProb pr = g.probs[blockIdx.y];
+    const int tm_n = (pr.M + 63) >> 6, tn_n = (pr.N + 63) >> 6;
+    if ((int)blockIdx.x >= tm_n * tn_n) return;
+    const int tm = blockIdx.x / tn_n, tn = blockIdx.x - tm * tn_n;
+    if ((pr.flags & (GEMM_SYMMETRIC | GEMM_LOWER_ONLY)) && tn > tm) return;
+    const int b = blockIdx.z;
+    const double *A = g.A + (size_t)b * g.strideA + pr.a_off, *B = g.B + (size_t)b * g.strideB + pr.b_off;
+    const double *sc = g.scale ? g.scale + (size_t)b * g.strideS + pr.s_off : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int m0 = tm * 64, n0 = tn * 64;
+    const int lr = tid >> 4, lc = tid & 15;          // loader: rows lr + 8 j, column lc of the chunk
+    double ra[8], rb[8];
+    auto fetch = [&](int k0) {
+        const int kk = k0 + lc;
+        const bool kin = kk < pr.K;
+        const double s = (sc && kin) ? sc[kk] : 1.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int m = m0 + lr + 8 * j, n = n0 + lr + 8 * j;
+            ra[j] = (kin && m < pr.M) ? A[(size_t)m * g.lda + kk] : 0.0;
+            rb[j] = (kin && n < pr.N) ? B[(size_t)n * g.ldb + kk] * s : 0.0;
+        }
+    };
+    double acc[4][4][2] = {};
+    fetch(0);
+    int buf = 0;
+    for (int k0 = 0; k0 < pr.K; k0 += 16, buf ^= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            As[buf][lr + 8 * j][lc] = ra[j];
+            Bs[buf][lr + 8 * j][lc] = rb[j];
+        }
+        __syncthreads();
+        if (k0 + 16 < pr.K) fetch(k0 + 16);
+#pragma unroll
+        for (int k4 = 0; k4 < 16; k4 += 4) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bb[j] = Bs[buf][wn * 32 + j * 8 + fr][k4 + fk];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        }
+    }
+    const size_t cb = (size_t)(g.cmap ? g.cmap[b] : b) * g.strideC + pr.c_off;
+    const double *dd = g.dadd ? g.dadd + (size_t)b * g.strideD + pr.d_off : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int m = m0 + wm * 32 + i * 8 + fr, n = n0 + wn * 32 + j * 8 + 2 * fk + e;
+                if (m >= pr.M || n >= pr.N) continue;
+                double v = acc[i][j][e];
+                if (m == n) {
+                    if (pr.flags & GEMM_ADD_IDENTITY) v += 1.0;
+                    if (dd) v += g.dadd_alpha * dd[m];
+                }
+                g.C[cb + (size_t)m * g.ldc + n] = v;
+                if ((pr.flags & GEMM_SYMMETRIC) && tn < tm) g.C[cb + (size_t)n * g.ldc + m] = v;
+            }
+}
+
+// Zd[slot][c][a] = (L_b^-1)[c][a] from the packed-upper tiles ZT = L_b^-T (row-major r x r, lower triangular)
+__global__ void zt_to_dense_lower_kernel(const double *__restrict__ ZT, int nb, int r, double *__restrict__ Zd) {
+    const int slot = blockIdx.y;
+    const double *Zs = ZT + (size_t)slot * ((size_t)nb * (nb + 1) / 2) * PGPFA_TILE;
+    double *out = Zd + (size_t)slot * r * r;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)r * r; e += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e / r), a = (int)(e - (size_t)c * r);
+        out[e] = (a <= c) ? Zs[utile(a >> 6, c >> 6, nb) * PGPFA_TILE + tile_off(a & 63, c & 63)] : 0.0;
+    }
+}
+
+// Y[(k,t), :] = sum_l P_t[k,l] Yh[(l,t), :]   in place, one CTA per (bin, slot)
+template <int Q>
+__global__ void __launch_bounds__(128) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r) {
+    __shared__ double Ps[Q * Q];
+    const int t = blockIdx.x, slot = blockIdx.y;
+    for (int i = threadIdx.x; i < Q * Q; i += blockDim.x) Ps[i] = Pm[((size_t)slot * Q * Q + i) * T + t];
+    __syncthreads();
+    double *Ys = Y + (size_t)slot * Q * T * r;
+    for (int c = threadIdx.x; c < r; c += blockDim.x) {
+        double v[Q], o[Q];
+#pragma unroll
+        for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            double s = 0.0;
+#pragma unroll
+            for (int l = 0; l < Q; l++) s += Ps[k * Q + l] * v[l];
+            o[k] = s;
+        }
+#pragma unroll
+        for (int k = 0; k < Q; k++) Ys[((size_t)k * T + t) * r + c] = o[k];
+    }
+}
+
+// post_vsm[trial][t][k][l] = eps P_t[k,l] + sum_c Y[(k,t),c] Y[(l,t),c]     one CTA (4 warps) per (bin, slot)
+template <int Q>
+__global__ void __launch_bounds__(128) lr_vsm_kernel(const double *__restrict__ Y, const double *__restrict__ Pm,
+                                                     const int *__restrict__ act, int T, int r, double eps,
+                                                     double *__restrict__ vsm) {
+    extern __shared__ double ys[];      // Q x r
+    const int t = blockIdx.x, slot = blockIdx.y, trial = act ? act[slot] : slot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *Ys = Y + (size_t)slot * Q * T * r;
+    for (int i = threadIdx.x; i < Q * r; i += blockDim.x) {
+        const int k = i / r, c = i - k * r;
+        ys[i] = Ys[((size_t)k * T + t) * r + c];
+    }
+    __syncthreads();
+    double *out = vsm + ((size_t)trial * T + t) * Q * Q;
+    for (int pidx = warp; pidx < Q * (Q + 1) / 2; pidx += 4) {
+        int k = 0;
+        while ((k + 1) * (k + 2) / 2 <= pidx) k++;
+        const int l = pidx - k * (k + 1) / 2;
+        double s = 0.0;
+        for (int c = lane; c < r; c += 32) s += ys[k * r + c] * ys[l * r + c];
+        s = warp_sum(s);
+        if (lane == 0) {
+            const double v = s + eps * Pm[((size_t)slot * Q * Q + k * Q + l) * T + t];
+            out[k * Q + l] = v;
+            out[l * Q + k] = v;
+        }
+    }
+}
+
+// u[slot][c] = sum_row Y[row][c] g[trial][row]
+__global__ void __launch_bounds__(128) lr_ytg_kernel(const double *__restrict__ Y, const double *__restrict__ gvec,
+                                                     const int *__restrict__ act, int n, int r, double *__restrict__ u) {
+    const int slot = blockIdx.y, trial = act ? act[slot] : slot;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= r) return;
+    const double *Ys = Y + (size_t)slot * n * r + c;
+    const double *gt = gvec + (size_t)trial * n;
+    double s0 = 0.0, s1 = 0.0;
+    int row = 0;
+    for (; row + 1 < n; row += 2) {
+        s0 += Ys[(size_t)row * r] * gt[row];
+        s1 += Ys[(size_t)(row + 1) * r] * gt[row + 1];
+    }
+    if (row < n) s0 += Ys[(size_t)row * r] * gt[row];
+    u[(size_t)slot * r + c] = s0 + s1;
+}
+
+// dx[trial][(k,t)] = -( eps sum_l P_t[k,l] g[(l,t)] + sum_c Y[(k,t),c] u[c] )       warp per row
+template <int Q>
+__global__ void __launch_bounds__(256) lr_step_kernel(const double *__restrict__ Y, const double *__restrict__ u,
+                                                      const double *__restrict__ Pm, const double *__restrict__ gvec,
+                                                      const int *__restrict__ act, int T, int r, double eps,
+                                                      double *__restrict__ dx) {
+    const int slot = blockIdx.y, trial = act ? act[slot] : slot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = Q * T;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= n) return;
+    const int k = row / T, t = row - k * T;
+    const double *yr = Y + ((size_t)slot * n + row) * r, *us = u + (size_t)slot * r;
+    double s = 0.0;
+    for (int c = lane; c < r; c += 32) s += yr[c] * us[c];
+    s = warp_sum(s);
+    if (lane == 0) {
+        double pg = 0.0;
+#pragma unroll
+        for (int l = 0; l < Q; l++)
+            pg += Pm[((size_t)slot * Q * Q + k * Q + l) * T + t] * gvec[(size_t)trial * n + (size_t)l * T + t];
+        dx[(size_t)trial * n + row] = -(eps * pg + s);
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+extern "C" int pgpfa_prior_lowrank(const double *K, int q, int T, double eps, double delta, double *F, double *Ft,
+                                   int *rank, cudaStream_t st) {
+    if (!K || !F || !Ft || !rank || q <= 0 || T <= 0 || !(delta > 0.0)) return PGPFA_ERR_ARG;
+    PGPFA_CUDA_TRY(cudaMemsetAsync(F, 0, (size_t)q * T * T * 8, st));
+    PGPFA_CUDA_TRY(cudaMemsetAsync(Ft, 0, (size_t)q * T * T * 8, st));
+    const size_t smem = (size_t)2 * T * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(pivchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pivchol_kernel<<<q, 256, smem, st>>>(K, T, eps, delta, F, Ft, rank);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+size_t pgpfa_i_lowrank_bytes_per_slot(int q, int T, int r) {
+    const int nbr = pgpfa_nb(r);
+    const size_t tiles = (size_t)(2 * pgpfa_ltiles(nbr) + nbr) * PGPFA_TILE * 8;
+    return align_up(tiles) + 2 * align_up((size_t)r * r * 8) + align_up((size_t)q * T * r * 8) +
+           2 * align_up((size_t)q * q * T * 8) + align_up((size_t)r * 8) + 4096;
+}
+
+namespace {
+template <int Q>
+int lr_launch_bins(const double *W, const int *act, int T, double eps, double *Pm, double *Dm, int nslots, cudaStream_t st) {
+    dim3 grid((T + 127) / 128, nslots);
+    lr_bins_kernel<Q><<<grid, 128, 0, st>>>(W, act, T, eps, Pm, Dm);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int Q>
+int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st) {
+    dim3 grid(T, nslots);
+    lr_mix_kernel<Q><<<grid, 128, 0, st>>>(Y, Pm, T, r);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int Q>
+int lr_launch_vsm(const double *Y, const double *Pm, const int *act, int T, int r, double eps, double *vsm, int nslots,
+                  cudaStream_t st) {
+    const size_t smem = (size_t)Q * r * sizeof(double);
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(lr_vsm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(T, nslots);
+    lr_vsm_kernel<Q><<<grid, 128, smem, st>>>(Y, Pm, act, T, r, eps, vsm);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int Q>
+int lr_launch_step(const double *Y, const double *u, const double *Pm, const double *g, const int *act, int T, int r,
+                   double eps, double *dx, int nslots, cudaStream_t st) {
+    dim3 grid((Q * T + 7) / 8, nslots);
+    lr_step_kernel<Q><<<grid, 256, 0, st>>>(Y, u, Pm, g, act, T, r, eps, dx);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int launch_gemm(const GemmArgs &g, const GemmProb *dprobs, int nprobs, int max_tiles, int batch, cudaStream_t st) {
+    if (nprobs == 0 || max_tiles == 0 || batch <= 0) return PGPFA_OK;
+    GemmArgs a = g;
+    a.probs = dprobs;
+    dim3 grid(max_tiles, nprobs, batch);
+    gemm_nt_kernel<<<grid, 128, 0, st>>>(a);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+// the three problem tables of a posterior pass: capacitance blocks, Yh per latent, T x T block per latent
+struct LrTables {
+    std::vector<GemmProb> cap, yh, blk;
+    int cap_tiles, yh_tiles, blk_tiles;
+};
+int max_tiles(const std::vector<GemmProb> &v) {
+    int t = 0;
+    for (const GemmProb &p : v) t = std::max(t, ((p.M + 63) / 64) * ((p.N + 63) / 64));
+    return t;
+}
+LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
+    LrTables tb;
+    const int r = lr.r;
+    for (int k = 0; k < q; k++)
+        for (int l = 0; l <= k; l++) {
+            if (lr.rank[k] == 0 || lr.rank[l] == 0) continue;
+            GemmProb pb;
+            pb.a_off = (long long)k * T * T; pb.b_off = (long long)l * T * T;
+            pb.c_off = (long long)lr.off[k] * r + lr.off[l];
+            pb.s_off = (long long)(k * q + l) * T; pb.d_off = 0;
+            pb.M = lr.rank[k]; pb.N = lr.rank[l]; pb.K = T;
+            pb.flags = (k == l) ? (GEMM_ADD_IDENTITY | GEMM_LOWER_ONLY) : 0;
+            tb.cap.push_back(pb);
+        }
+    for (int l = 0; l < q; l++) {
+        GemmProb pb;
+        pb.a_off = (long long)l * T * T; pb.b_off = lr.off[l]; pb.c_off = (long long)l * T * r;
+        pb.s_off = 0; pb.d_off = 0;
+        pb.M = T; pb.N = r; pb.K = lr.rank[l]; pb.flags = 0;
+        tb.yh.push_back(pb);
+    }
+    for (int k = 0; k < q; k++) {
+        GemmProb pb;
+        pb.a_off = (long long)k * T * r; pb.b_off = pb.a_off; pb.c_off = (long long)k * T * T;
+        pb.s_off = 0; pb.d_off = (long long)(k * q + k) * T;
+        pb.M = T; pb.N = T; pb.K = r; pb.flags = GEMM_SYMMETRIC;
+        tb.blk.push_back(pb);
+    }
+    tb.cap_tiles = max_tiles(tb.cap); tb.yh_tiles = max_tiles(tb.yh); tb.blk_tiles = max_tiles(tb.blk);
+    return tb;
+}
+}  // namespace
+
+#define LR_DISPATCH(FN, ...)                                   \
+    switch (q) {                                               \
+        LR_CASES(FN, __VA_ARGS__)                              \
+        default: return PGPFA_ERR_ARG;                         \
+    }
+#define LR_CASE(QQ, FN, ...) case QQ: PGPFA_TRY(FN<QQ>(__VA_ARGS__)); break;
+#define LR_CASES(FN, ...)                                                                                           \
+    LR_CASE(1, FN, __VA_ARGS__) LR_CASE(2, FN, __VA_ARGS__) LR_CASE(3, FN, __VA_ARGS__) LR_CASE(4, FN, __VA_ARGS__)  \
+    LR_CASE(5, FN, __VA_ARGS__) LR_CASE(6, FN, __VA_ARGS__) LR_CASE(7, FN, __VA_ARGS__) LR_CASE(8, FN, __VA_ARGS__)  \
+    LR_CASE(9, FN, __VA_ARGS__) LR_CASE(10, FN, __VA_ARGS__) LR_CASE(11, FN, __VA_ARGS__) LR_CASE(12, FN, __VA_ARGS__)
+
+// Uploads the problem tables of the posterior pass (once per E-step; they depend only on the ranks).
+int pgpfa_i_lowrank_prepare(const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st) {
+    const LrTables tb = lr_tables(lr, q, T);
+    const size_t qq = (size_t)q * (q + 1);
+    if (3 * qq * sizeof(GemmProb) > PGPFA_LOWRANK_TABLE_BYTES) return PGPFA_ERR_WORKSPACE;
+    GemmProb *d = static_cast<GemmProb *>(probs_dev);
+    if (!tb.cap.empty())
+        PGPFA_CUDA_TRY(cudaMemcpyAsync(d, tb.cap.data(), tb.cap.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(d + qq, tb.yh.data(), tb.yh.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(d + 2 * qq, tb.blk.data(), tb.blk.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));      // the tables are host temporaries
+    return PGPFA_OK;
+}
+
+// Posterior pass of one chunk of trials through the low-rank prior factor.  `area` is scratch of at least
+// nslots * pgpfa_i_lowrank_bytes_per_slot(q, T, r) bytes; `probs_dev` was filled by pgpfa_i_lowrank_prepare.
+// Order: per-bin matrices, capacitance matrix, its factorisation and triangular inverse, Y, polishing Newton step,
+// time-diagonal blocks (event `ev_means` is recorded here: x / vsm final), then the T x T blocks of every latent.
+int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
+                              double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
+                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st) {
+    if (nslots <= 0) return PGPFA_OK;
+    const int r = lr.r, n = q * T, nbr = pgpfa_nb(r);
+    const long long ltr = pgpfa_ltiles(nbr);
+    unsigned char *p = static_cast<unsigned char *>(area);
+    auto take = [&](size_t bytes) { unsigned char *o = p; p += align_up(bytes); return o; };
+    double *Lr = (double *)take((size_t)nslots * ltr * PGPFA_TILE * 8);
+    double *Dr = (double *)take((size_t)nslots * nbr * PGPFA_TILE * 8);
+    double *Zr = (double *)take((size_t)nslots * ltr * PGPFA_TILE * 8);
+    double *G = (double *)take((size_t)nslots * r * r * 8);
+    double *Zd = (double *)take((size_t)nslots * r * r * 8);
+    double *Y = (double *)take((size_t)nslots * n * r * 8);
+    double *Pm = (double *)take((size_t)nslots * q * q * T * 8);
+    double *Dm = (double *)take((size_t)nslots * q * q * T * 8);
+    double *u = (double *)take((size_t)nslots * r * 8);
+    const GemmProb *dprobs = static_cast<const GemmProb *>(probs_dev);
+    const size_t qq = (size_t)q * (q + 1);
+    const LrTables tb = lr_tables(lr, q, T);
+
+    // ---- per-bin P, Dt; capacitance matrix G = I + F^T Dt F (lower block triangle, ragged blocks r_k x r_l)
+    pgpfa_prof_begin(h, PGPFA_PROF_LOWRANK, st);
+    LR_DISPATCH(lr_launch_bins, W, act, T, lr.eps, Pm, Dm, nslots, st)
+    {
+        GemmArgs g;
+        g.A = lr.Ft; g.B = lr.Ft; g.C = G; g.scale = Dm; g.dadd = nullptr;
+        g.strideA = 0; g.strideB = 0; g.strideC = (long long)r * r; g.strideS = (long long)q * q * T; g.strideD = 0;
+        g.lda = T; g.ldb = T; g.ldc = r; g.cmap = nullptr; g.probs = nullptr; g.dadd_alpha = 0.0;
+        PGPFA_TRY(launch_gemm(g, dprobs, (int)tb.cap.size(), tb.cap_tiles, nslots, st));
+    }
+    pgpfa_prof_end(h, st);
+    // ---- L_b L_b^T = G, Z_b = L_b^-1 (tile kernels of factor.cu on r x r matrices)
+    PgpfaMatSrc ms;
+    ms.Kinv = nullptr; ms.W = nullptr; ms.dense = G; ms.q = 1; ms.T = r; ms.n = r; ms.diag_scale = 1.0;
+    pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
+    PGPFA_TRY(pgpfa_i_factor(ms, Lr, Dr, Zr, nullptr, nullptr, nslots, st, h));
+    pgpfa_prof_end(h, st);
+    h->prof_work[PGPFA_PROF_FACTOR] += (double)nslots * r * (double)r * r / 3.0;
+    pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);
+    PGPFA_TRY(pgpfa_i_trtri(Lr, Dr, Zr, r, nslots, st, h));
+    pgpfa_prof_end(h, st);
+    h->prof_work[PGPFA_PROF_TRTRI] += (double)nslots * r * (double)r * r / 3.0;
+    pgpfa_prof_begin(h, PGPFA_PROF_LOWRANK, st);
+    {
+        dim3 grid(64, nslots);
+        zt_to_dense_lower_kernel<<<grid, 256, 0, st>>>(Zr, nbr, r, Zd);
+        PGPFA_LAUNCH_CHECK();
+    }
+    // ---- Yh[(l,t), c] = sum_a F_l[t][a] Z_b[c][off_l + a], then Y = P Yh per bin
+    {
+        GemmArgs g;
+        g.A = lr.F; g.B = Zd; g.C = Y; g.scale = nullptr; g.dadd = nullptr;
+        g.strideA = 0; g.strideB = (long long)r * r; g.strideC = (long long)n * r; g.strideS = 0; g.strideD = 0;
+        g.lda = T; g.ldb = r; g.ldc = r; g.cmap = nullptr; g.probs = nullptr; g.dadd_alpha = 0.0;
+        PGPFA_TRY(launch_gemm(g, dprobs + qq, (int)tb.yh.size(), tb.yh_tiles, nslots, st));
+    }
+    LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st)
+    // ---- polishing Newton step  dx = -Sigma g = -(eps P g + Y (Y^T g))
+    {
+        dim3 grid((r + 127) / 128, nslots);
+        lr_ytg_kernel<<<grid, 128, 0, st>>>(Y, gvec, act, n, r, u);
+        PGPFA_LAUNCH_CHECK();
+    }
+    LR_DISPATCH(lr_launch_step, Y, u, Pm, gvec, act, T, r, lr.eps, dx, nslots, st)
+    PGPFA_TRY(pgpfa_i_polish(x, dx, act, n, 1e3 * tol, steplen, nslots, st));
+    // ---- slices
+    if (vsm) LR_DISPATCH(lr_launch_vsm, Y, Pm, act, T, r, lr.eps, vsm, nslots, st)
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
+    if (vsmGP) {
+        GemmArgs g;
+        g.A = Y; g.B = Y; g.C = vsmGP; g.scale = nullptr; g.dadd = Pm;
+        g.strideA = (long long)n * r; g.strideB = g.strideA; g.strideC = (long long)q * T * T; g.strideS = 0;
+        g.strideD = (long long)q * q * T;
+        g.lda = r; g.ldb = r; g.ldc = T; g.cmap = act; g.probs = nullptr; g.dadd_alpha = lr.eps;
+        PGPFA_TRY(launch_gemm(g, dprobs + 2 * qq, (int)tb.blk.size(), tb.blk_tiles, nslots, st));
+    }
+    pgpfa_prof_end(h, st);
+    return PGPFA_OK;
+}

@@ -41,6 +41,7 @@ enum {
     PGPFA_PROF_TRTRI = 3,     // triangular inverse; work = trials * n^3/3 flops
     PGPFA_PROF_SLICES = 4,    // time-diagonals + selected inverse tiles
     PGPFA_PROF_BLOCKFACTOR = 5,  // CG preconditioner set-up (q shared T x T inverses per E-step)
+    PGPFA_PROF_LOWRANK = 6,      // low-rank posterior pass: per-bin matrices, capacitance GEMM, Y, slices (lowrank.cu)
     PGPFA_PROF_SLOTS = 8
 };
 #define PGPFA_MAX_PARTS 4
@@ -78,5 +79,21 @@ int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const doub
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);
+int pgpfa_i_polish(double *x, const double *dx, const int *act, int n, double max_rel, double *steplen, int nslots,
+                   cudaStream_t st);
+
+// low-rank factor of the smooth part of the prior, K_k - eps I = F_k F_k^T (lowrank.cu)
+struct PgpfaLowRank {
+    const double *F, *Ft;            // (q,T,T): [k][t][a] and [k][a][t], columns / rows >= rank[k] zero
+    int rank[PGPFA_QMAX], off[PGPFA_QMAX + 1];
+    int r;                           // sum of the ranks
+    double eps;
+};
+#define PGPFA_LOWRANK_TABLE_BYTES 65536
+size_t pgpfa_i_lowrank_bytes_per_slot(int q, int T, int r);
+int pgpfa_i_lowrank_prepare(const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st);
+int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
+                              double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
+                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st);
 int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st);
 int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st);

@@ -178,9 +178,20 @@ class LaplaceResult:
     __slots__ = ("x", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc")
 
 
+def prior_lowrank(K, eps=0.001, delta=1e-14):
+    """Pivoted Cholesky K_k - eps I = F_k F_k^T (pgpfa_prior_lowrank).  Returns (F, Ft, ranks) with ranks a host list."""
+    q, T, _ = K.shape
+    F, Ft = empty(q, T, T), empty(q, T, T)
+    rank = empty(q, dtype=torch.int32)
+    call("pgpfa_prior_lowrank", ptr(K), q, T, float(eps), float(delta), ptr(F), ptr(Ft), ptr(rank), stream())
+    return F, Ft, [int(v) for v in rank.cpu().tolist()]
+
+
 def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True, want_vsmGP=True, want_cov=False,
-                  max_ws_bytes=None, ws=None, inexact_newton=True):
-    """Batched Newton E-step (pgpfa_laplace_solve). y (R,N,T); returns LaplaceResult with device tensors."""
+                  max_ws_bytes=None, ws=None, inexact_newton=True, lowrank=None):
+    """Batched Newton E-step (pgpfa_laplace_solve). y (R,N,T); returns LaplaceResult with device tensors.
+    lowrank = (F, Ft, ranks, eps) from prior_lowrank: posterior pass through the low-rank prior factor
+    (pgpfa_laplace_solve_lowrank; not with want_cov)."""
     R, N, T = y.shape
     q = C.shape[1]
     x = torch.zeros(R, q, T, dtype=torch.float64, device="cuda") if x0 is None else x0.clone()
@@ -202,12 +213,20 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
             nbytes = max(max_ws_bytes, _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, 1))
         ws = workspace(nbytes)
     stats = (ctypes.c_int * 8)()
-    res.rc = call("pgpfa_laplace_solve", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(x), R, q, N, T, float(tol),
-                  int(max_newton), int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov), ptr(res.niter),
-                  ptr(res.info), ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(),
-                  allow=(_lib.ERR_NOT_CONVERGED,))
+    if lowrank is not None and not want_cov:
+        F, Ft, ranks, eps = lowrank
+        rank_host = (ctypes.c_int * q)(*[int(v) for v in ranks])
+        res.rc = call("pgpfa_laplace_solve_lowrank", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(F), ptr(Ft),
+                      ctypes.cast(rank_host, ctypes.c_void_p), float(eps), ptr(x), R, q, N, T, float(tol), int(max_newton),
+                      int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.niter), ptr(res.info),
+                      ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(), allow=(_lib.ERR_NOT_CONVERGED,))
+    else:
+        res.rc = call("pgpfa_laplace_solve", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(x), R, q, N, T, float(tol),
+                      int(max_newton), int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov),
+                      ptr(res.niter), ptr(res.info), ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(),
+                      allow=(_lib.ERR_NOT_CONVERGED,))
     res.stats = {"factorizations": stats[0], "max_newton_iters": stats[1], "not_converged": stats[2],
-                 "chunk": stats[3], "pcg_newton_iters": stats[4], "fallback_trials": stats[5],
+                 "chunk": stats[3], "pcg_newton_iters": stats[4], "fallback_trials": stats[5], "lowrank_r": stats[6],
                  "fresh_chord_sweeps": stats[7] % 1000, "pcg_iters": stats[7] // 1000}
     return res
 

@@ -113,7 +113,8 @@ def test_full_shape_properties():
     pt = torch.as_tensor(perm, device="cuda")
     assert torch.equal(est2.x, est.x[pt]) and torch.equal(est2.vsm, est.vsm[pt]) and torch.equal(est2.vsmGP, est.vsmGP[pt])
     small = _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, 40)
-    res3 = kn.laplace_solve(trials.y, p.C, p.d, p.Kinv, max_ws_bytes=small)
+    res3 = kn.laplace_solve(trials.y, p.C, p.d, p.Kinv, max_ws_bytes=small, lowrank=p.lowrank)
+    assert res3.stats["lowrank_r"] == est.stats["lowrank_r"] > 0
     assert res3.stats["chunk"] == 40
     assert torch.equal(res3.x, est.x) and torch.equal(res3.vsm, est.vsm) and torch.equal(res3.vsmGP, est.vsmGP)
     # (4) sufficient statistics are additive over trial blocks (what the multi-GPU all-reduce relies on)
