@@ -240,29 +240,50 @@ def run_ours(args):
     except Exception:
         pass
     fp64_peak = float(peaks.get("fp64_roofline_peak_tflops", 35.4))
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_factor_traffic.json")))["dram_bytes_per_factorisation"]
-        traffic = traffic * (hi - lo) / 1024.0          # captured at 1024 trials per GPU
-    except Exception:
-        pass
-    fac_ms, fac_flops, fac_cnt = prof_ms[0], prof_work[0], prof_cnt[0]
-    achieved = fac_flops / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "batched Cholesky call (chol_diag_kernel + chol_panel_kernel launches, DMMA.8x8x4); a launch = one factorisation of all trials of the rank",
-                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": traffic,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one factorisation call, "
-                                  "ncu launch list of this command (profiles/r01_factor_traffic.json), scaled to this rank's "
-                                  "trial count",
-                "peak_source": "measured cuBLAS DGEMM 8192^3 sustained on this pool (profiles/r01_fp64_peaks.json); "
-                               "MEASURED_PEAKS.json has no FP64 line",
-                "algorithmic_flops_per_launch": fac_flops / max(fac_cnt, 1), "launches": int(fac_cnt),
-                "share_of_step": fac_ms / ms,
-                "other_ms_per_step": {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
-                                      "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
-                                      "factor": fac_ms / args.steps, "cg_preconditioner_setup": prof_ms[5] / args.steps},
-                "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
-                "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
+    lowrank_r = int(est.stats.get("lowrank_r", 0))
+    other = {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
+             "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
+             "factor": prof_ms[0] / args.steps, "cg_preconditioner_setup": prof_ms[5] / args.steps,
+             "lowrank_posterior_other": prof_ms[6] / args.steps}
+
+    def traffic_of(fname, key):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", fname)))[key] * (hi - lo) / 1024.0   # captured at 1024 trials
+        except Exception:
+            return None
+
+    peak_src = ("measured cuBLAS DGEMM 8192^3 sustained on this pool (profiles/r01_fp64_peaks.json); "
+                "MEASURED_PEAKS.json has no FP64 line")
+    if lowrank_r > 0:
+        # low-rank posterior pass (csrc/lowrank.cu): the dominant launch is the batched symmetric product
+        # post_vsmGP[k] = eps diag(P) + Y_k Y_k^T (gemm_nt_kernel, q x trials problems of T x T x r)
+        k_ms, k_flops, k_cnt = prof_ms[4], prof_work[4], prof_cnt[4]
+        achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        roofline = {"bound": "tensor",
+                    "kernel": "gemm_nt_kernel, the post_vsmGP launch (q*trials symmetric T x T x r products Y_k Y_k^T on DMMA.8x8x4); "
+                              "r = %d is the rank of the prior factor; the C,d M-step runs concurrently on a second stream" % lowrank_r,
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                    "traffic": traffic_of("r01_syrk_traffic.json", "dram_bytes_per_launch"),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full capture "
+                                      "(profiles/r01_syrk_traffic.json), scaled to this rank's trial count",
+                    "peak_source": peak_src,
+                    "algorithmic_flops_per_launch": k_flops / max(k_cnt, 1), "launches": int(k_cnt),
+                    "share_of_step": k_ms / ms, "other_ms_per_step": other,
+                    "rxr_cholesky_tflops": prof_work[0] / (prof_ms[0] * 1e-3) / 1e12 if prof_ms[0] > 0 else None}
+    else:
+        fac_ms, fac_flops, fac_cnt = prof_ms[0], prof_work[0], prof_cnt[0]
+        achieved = fac_flops / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "batched Cholesky call (chol_diag_kernel + chol_panel_kernel launches, DMMA.8x8x4); a launch = one factorisation of all trials of the rank",
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                    "traffic": traffic_of("r01_factor_traffic.json", "dram_bytes_per_factorisation"),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one factorisation call, "
+                                      "ncu launch list of this command (profiles/r01_factor_traffic.json), scaled to this rank's "
+                                      "trial count",
+                    "peak_source": peak_src,
+                    "algorithmic_flops_per_launch": fac_flops / max(fac_cnt, 1), "launches": int(fac_cnt),
+                    "share_of_step": fac_ms / ms, "other_ms_per_step": other,
+                    "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
+                    "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
     cpu = None
     if not args.skip_cpu and not args.profile_mode and world == 1:
         sec, _ = cpu_sample(w, args.cpu_trials, 1, 1)
@@ -275,8 +296,11 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: synthetic q=8 N=100 T=200 R=%d full-batch Laplace EM, steady-state "
                                    "(warm-started) iterations" % R,
-                       "trials_per_gpu": hi - lo, "l2": "working set (factor tiles %.1f GB/GPU) >> L2, no flush needed"
-                                                        % ((hi - lo) * 2 * 10.65e6 / 1e9),
+                       "posterior_pass": ("low-rank prior factor, r=%d of qT=%d" % (lowrank_r, n)) if lowrank_r else "dense tiled Cholesky",
+                       "trials_per_gpu": hi - lo,
+                       "l2": ("working set (Y, post_vsmGP, counts: %.1f GB/GPU) >> L2, no flush needed"
+                              % ((hi - lo) * (n * lowrank_r + q * T * T + N * T) * 8 / 1e9)) if lowrank_r else
+                             ("working set (factor tiles %.1f GB/GPU) >> L2, no flush needed" % ((hi - lo) * 2 * 10.65e6 / 1e9)),
                        "newton_tol": 1e-8},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": 1.0 / e2e_sec, "unit": "EM iters/s", "h2d_bytes_per_step": int(h2d),

@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmArgs g) {
         }
     };
     double acc[4][4][2] = {};
+    // 8-row / 8-column blocks of this warp's 32 x 32 patch that hold rows < M / columns < N (ragged edges are common:
+    // T = 200 is 3 tiles + 8 rows, the rank blocks are 10-60 wide)
+    const int mi = min(4, max(0, (pr.M - m0 - wm * 32 + 7) >> 3)), nj = min(4, max(0, (pr.N - n0 - wn * 32 + 7) >> 3));
     fetch(0);
     int buf = 0;
     for (int k0 = 0; k0 < pr.K; k0 += 16, buf ^= 1) {
@@ -234,17 +237,20 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmArgs g) {
         }
         __syncthreads();
         if (k0 + 16 < pr.K) fetch(k0 + 16);
+        if (mi > 0 && nj > 0) {
 #pragma unroll
-        for (int k4 = 0; k4 < 16; k4 += 4) {
-            double a[4], bb[4];
+            for (int k4 = 0; k4 < 16; k4 += 4) {
+                double a[4], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
+                for (int i = 0; i < 4; i++) a[i] = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
 #pragma unroll
-            for (int j = 0; j < 4; j++) bb[j] = Bs[buf][wn * 32 + j * 8 + fr][k4 + fk];
+                for (int j = 0; j < 4; j++) bb[j] = Bs[buf][wn * 32 + j * 8 + fr][k4 + fk];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+                    for (int j = 0; j < 4; j++)
+                        if (i < mi && j < nj) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+            }
         }
     }
     const size_t cb = (size_t)(g.cmap ? g.cmap[b] : b) * g.strideC + pr.c_off;
@@ -278,15 +284,21 @@ __global__ void zt_to_dense_lower_kernel(const double *__restrict__ ZT, int nb, 
     }
 }
 
-// Y[(k,t), :] = sum_l P_t[k,l] Yh[(l,t), :]   in place, one CTA per (bin, slot)
+// Y[(k,t), :] = sum_l P_t[k,l] Yh[(l,t), :]   in place; one CTA handles LR_TB consecutive bins of a slot
+#define LR_TB 8
 template <int Q>
-__global__ void __launch_bounds__(128) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r) {
-    __shared__ double Ps[Q * Q];
-    const int t = blockIdx.x, slot = blockIdx.y;
-    for (int i = threadIdx.x; i < Q * Q; i += blockDim.x) Ps[i] = Pm[((size_t)slot * Q * Q + i) * T + t];
+__global__ void __launch_bounds__(256) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r) {
+    __shared__ double Ps[LR_TB][Q * Q];
+    const int t0 = blockIdx.x * LR_TB, slot = blockIdx.y;
+    for (int i = threadIdx.x; i < LR_TB * Q * Q; i += blockDim.x) {
+        const int tl = i / (Q * Q), e = i - tl * Q * Q;
+        Ps[tl][e] = (t0 + tl < T) ? Pm[((size_t)slot * Q * Q + e) * T + t0 + tl] : 0.0;
+    }
     __syncthreads();
     double *Ys = Y + (size_t)slot * Q * T * r;
-    for (int c = threadIdx.x; c < r; c += blockDim.x) {
+    const int nt = min(LR_TB, T - t0);
+    for (int i = threadIdx.x; i < nt * r; i += blockDim.x) {
+        const int tl = i / r, c = i - tl * r, t = t0 + tl;
         double v[Q], o[Q];
 #pragma unroll
         for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(128) lr_mix_kernel(double *__restrict__ Y, con
         for (int k = 0; k < Q; k++) {
             double s = 0.0;
 #pragma unroll
-            for (int l = 0; l < Q; l++) s += Ps[k * Q + l] * v[l];
+            for (int l = 0; l < Q; l++) s += Ps[tl][k * Q + l] * v[l];
             o[k] = s;
         }
 #pragma unroll
@@ -302,34 +314,49 @@ __global__ void __launch_bounds__(128) lr_mix_kernel(double *__restrict__ Y, con
     }
 }
 
-// post_vsm[trial][t][k][l] = eps P_t[k,l] + sum_c Y[(k,t),c] Y[(l,t),c]     one CTA (4 warps) per (bin, slot)
+// post_vsm[trial][t][k][l] = eps P_t[k,l] + sum_c Y[(k,t),c] Y[(l,t),c]: the q x q Gram matrix of the q rows of Y that
+// belong to bin t, one warp per bin on the FP64 tensor pipe.  For m8n8k4 the A fragment (row = lane/4, k = lane%4) of a
+// matrix and the B fragment (k = lane%4, col = lane/4) of its transpose are the same register, so one 8-byte load per
+// lane and k-step feeds the MMA; Y is streamed from HBM exactly once.
 template <int Q>
-__global__ void __launch_bounds__(128) lr_vsm_kernel(const double *__restrict__ Y, const double *__restrict__ Pm,
+__global__ void __launch_bounds__(256) lr_vsm_kernel(const double *__restrict__ Y, const double *__restrict__ Pm,
                                                      const int *__restrict__ act, int T, int r, double eps,
                                                      double *__restrict__ vsm) {
-    extern __shared__ double ys[];      // Q x r
-    const int t = blockIdx.x, slot = blockIdx.y, trial = act ? act[slot] : slot;
+    constexpr int QB = (Q + 7) / 8;
+    const int slot = blockIdx.y, trial = act ? act[slot] : slot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *Ys = Y + (size_t)slot * Q * T * r;
-    for (int i = threadIdx.x; i < Q * r; i += blockDim.x) {
-        const int k = i / r, c = i - k * r;
-        ys[i] = Ys[((size_t)k * T + t) * r + c];
+    const int t = blockIdx.x * 8 + warp;
+    if (t >= T) return;
+    const int fr = lane >> 2, fk = lane & 3;
+    const double *rowp[QB];
+    bool rowok[QB];
+#pragma unroll
+    for (int bi = 0; bi < QB; bi++) {
+        const int row = bi * 8 + fr;
+        rowok[bi] = row < Q;
+        rowp[bi] = Y + ((size_t)slot * Q * T + (size_t)(rowok[bi] ? row : 0) * T + t) * r;
     }
-    __syncthreads();
+    double acc[QB][QB][2] = {};
+#pragma unroll 4
+    for (int k0 = 0; k0 < r; k0 += 4) {
+        double a[QB];
+#pragma unroll
+        for (int bi = 0; bi < QB; bi++) a[bi] = (rowok[bi] && k0 + fk < r) ? rowp[bi][k0 + fk] : 0.0;
+#pragma unroll
+        for (int bi = 0; bi < QB; bi++)
+#pragma unroll
+            for (int bj = 0; bj < QB; bj++) dmma884(acc[bi][bj][0], acc[bi][bj][1], a[bi], a[bj]);
+    }
     double *out = vsm + ((size_t)trial * T + t) * Q * Q;
-    for (int pidx = warp; pidx < Q * (Q + 1) / 2; pidx += 4) {
-        int k = 0;
-        while ((k + 1) * (k + 2) / 2 <= pidx) k++;
-        const int l = pidx - k * (k + 1) / 2;
-        double s = 0.0;
-        for (int c = lane; c < r; c += 32) s += ys[k * r + c] * ys[l * r + c];
-        s = warp_sum(s);
-        if (lane == 0) {
-            const double v = s + eps * Pm[((size_t)slot * Q * Q + k * Q + l) * T + t];
-            out[k * Q + l] = v;
-            out[l * Q + k] = v;
-        }
-    }
+#pragma unroll
+    for (int bi = 0; bi < QB; bi++)
+#pragma unroll
+        for (int bj = 0; bj < QB; bj++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int k = bi * 8 + fr, l = bj * 8 + 2 * fk + e;
+                if (k < Q && l < Q) out[k * Q + l] = acc[bi][bj][e] + eps * Pm[((size_t)slot * Q * Q + k * Q + l) * T + t];
+            }
 }
 
 // u[slot][c] = sum_row Y[row][c] g[trial][row]
@@ -410,19 +437,16 @@ int lr_launch_bins(const double *W, const int *act, int T, double eps, double *P
 }
 template <int Q>
 int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st) {
-    dim3 grid(T, nslots);
-    lr_mix_kernel<Q><<<grid, 128, 0, st>>>(Y, Pm, T, r);
+    dim3 grid((T + LR_TB - 1) / LR_TB, nslots);
+    lr_mix_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, T, r);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
 template <int Q>
 int lr_launch_vsm(const double *Y, const double *Pm, const int *act, int T, int r, double eps, double *vsm, int nslots,
                   cudaStream_t st) {
-    const size_t smem = (size_t)Q * r * sizeof(double);
-    if (smem > 48 * 1024)
-        PGPFA_CUDA_TRY(cudaFuncSetAttribute(lr_vsm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(T, nslots);
-    lr_vsm_kernel<Q><<<grid, 128, smem, st>>>(Y, Pm, act, T, r, eps, vsm);
+    dim3 grid((T + 7) / 8, nslots);
+    lr_vsm_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, act, T, r, eps, vsm);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -586,14 +610,18 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
     // ---- slices
     if (vsm) LR_DISPATCH(lr_launch_vsm, Y, Pm, act, T, r, lr.eps, vsm, nslots, st)
     PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
+    pgpfa_prof_end(h, st);
     if (vsmGP) {
+        pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
         GemmArgs g;
         g.A = Y; g.B = Y; g.C = vsmGP; g.scale = nullptr; g.dadd = Pm;
         g.strideA = (long long)n * r; g.strideB = g.strideA; g.strideC = (long long)q * T * T; g.strideS = 0;
         g.strideD = (long long)q * q * T;
         g.lda = r; g.ldb = r; g.ldc = T; g.cmap = act; g.probs = nullptr; g.dadd_alpha = lr.eps;
         PGPFA_TRY(launch_gemm(g, dprobs + 2 * qq, (int)tb.blk.size(), tb.blk_tiles, nslots, st));
+        pgpfa_prof_end(h, st);
+        // algorithmic work of the q symmetric T x T x r products: T (T+1) r flops each
+        h->prof_work[PGPFA_PROF_SLICES] += (double)nslots * q * (double)T * (T + 1) * r;
     }
-    pgpfa_prof_end(h, st);
     return PGPFA_OK;
 }
