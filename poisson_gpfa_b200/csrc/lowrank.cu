@@ -197,8 +197,24 @@ struct GemmArgs {
     double dadd_alpha;
 };
 
-__global__ void __launch_bounds__(128) gemm_nt_kernel(GemmArgs g) {
-    __shared__ double As[2][64][20], Bs[2][64][20];
+#define GN_STAGES 3
+#define GN_LD 20                                   // padded k-stride of a staged row (doubles)
+#define GN_STAGE_DOUBLES (2 * 64 * GN_LD + 16)     // A rows, B rows, 16 scale values
+#define GN_SMEM (GN_STAGES * GN_STAGE_DOUBLES * 8)
+
+// 8-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// K is consumed in chunks of 16 through a GN_STAGES-deep ring of shared-memory stages filled by cp.async, so the
+// global loads of the next two chunks are in flight while the current one is multiplied.
+__global__ void __launch_bounds__(128, 3) gemm_nt_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double gsm[];
     const GemmProb pr = g.probs[blockIdx.y];
     const int tm_n = (pr.M + 63) >> 6, tn_n = (pr.N + 63) >> 6;
     if ((int)blockIdx.x >= tm_n * tn_n) return;
@@ -211,40 +227,50 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(GemmArgs g) {
     const int fr = lane >> 2, fk = lane & 3;
     const int m0 = tm * 64, n0 = tn * 64;
     const int lr = tid >> 4, lc = tid & 15;          // loader: rows lr + 8 j, column lc of the chunk
-    double ra[8], rb[8];
-    auto fetch = [&](int k0) {
-        const int kk = k0 + lc;
+    // rows of this thread: lr + 8 j; out-of-range rows / columns are zero-filled by the copy (source clamped to row 0)
+    const double *abase = A + (size_t)(m0 + lr) * g.lda, *bbase = B + (size_t)(n0 + lr) * g.ldb;
+    const size_t astep = (size_t)8 * g.lda, bstep = (size_t)8 * g.ldb;
+    auto stage_load = [&](int chunk, int st) {
+        double *As = gsm + (size_t)st * GN_STAGE_DOUBLES, *Bs = As + 64 * GN_LD, *Ss = Bs + 64 * GN_LD;
+        const int kk = chunk * 16 + lc;
         const bool kin = kk < pr.K;
-        const double s = (sc && kin) ? sc[kk] : 1.0;
+        const int kc = kin ? kk : 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int m = m0 + lr + 8 * j, n = n0 + lr + 8 * j;
-            ra[j] = (kin && m < pr.M) ? A[(size_t)m * g.lda + kk] : 0.0;
-            rb[j] = (kin && n < pr.N) ? B[(size_t)n * g.ldb + kk] * s : 0.0;
+            const bool am = kin && (m0 + lr + 8 * j < pr.M), bn = kin && (n0 + lr + 8 * j < pr.N);
+            cp_async8(As + (lr + 8 * j) * GN_LD + lc, am ? abase + j * astep + kc : A, am ? 8 : 0);
+            cp_async8(Bs + (lr + 8 * j) * GN_LD + lc, bn ? bbase + j * bstep + kc : B, bn ? 8 : 0);
+        }
+        if (sc && tid < 16) {
+            const int ks = chunk * 16 + tid;
+            cp_async8(Ss + tid, sc + (ks < pr.K ? ks : 0), ks < pr.K ? 8 : 0);
         }
     };
     double acc[4][4][2] = {};
     // 8-row / 8-column blocks of this warp's 32 x 32 patch that hold rows < M / columns < N (ragged edges are common:
     // T = 200 is 3 tiles + 8 rows, the rank blocks are 10-60 wide)
     const int mi = min(4, max(0, (pr.M - m0 - wm * 32 + 7) >> 3)), nj = min(4, max(0, (pr.N - n0 - wn * 32 + 7) >> 3));
-    fetch(0);
-    int buf = 0;
-    for (int k0 = 0; k0 < pr.K; k0 += 16, buf ^= 1) {
+    const int nchunks = (pr.K + 15) >> 4;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            As[buf][lr + 8 * j][lc] = ra[j];
-            Bs[buf][lr + 8 * j][lc] = rb[j];
-        }
-        __syncthreads();
-        if (k0 + 16 < pr.K) fetch(k0 + 16);
+    for (int s0 = 0; s0 < GN_STAGES - 1; s0++) {
+        if (s0 < nchunks) stage_load(s0, s0);
+        cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<GN_STAGES - 2>();
+        __syncthreads();                    // chunk c has landed for everyone; stage (c-1) % GN_STAGES is free again
+        if (c + GN_STAGES - 1 < nchunks) stage_load(c + GN_STAGES - 1, (c + GN_STAGES - 1) % GN_STAGES);
+        cp_async_commit();
+        const double *As = gsm + (size_t)(c % GN_STAGES) * GN_STAGE_DOUBLES, *Bs = As + 64 * GN_LD, *Ss = Bs + 64 * GN_LD;
         if (mi > 0 && nj > 0) {
 #pragma unroll
             for (int k4 = 0; k4 < 16; k4 += 4) {
                 double a[4], bb[4];
+                const double sv = sc ? Ss[k4 + fk] : 1.0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[buf][wm * 32 + i * 8 + fr][k4 + fk];
+                for (int i = 0; i < 4; i++) a[i] = As[(wm * 32 + i * 8 + fr) * GN_LD + k4 + fk] * sv;
 #pragma unroll
-                for (int j = 0; j < 4; j++) bb[j] = Bs[buf][wn * 32 + j * 8 + fr][k4 + fk];
+                for (int j = 0; j < 4; j++) bb[j] = Bs[(wn * 32 + j * 8 + fr) * GN_LD + k4 + fk];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -464,7 +490,12 @@ int launch_gemm(const GemmArgs &g, const GemmProb *dprobs, int nprobs, int max_t
     GemmArgs a = g;
     a.probs = dprobs;
     dim3 grid(max_tiles, nprobs, batch);
-    gemm_nt_kernel<<<grid, 128, 0, st>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_SMEM));
+        attr_set = true;
+    }
+    gemm_nt_kernel<<<grid, 128, GN_SMEM, st>>>(a);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
