@@ -32,7 +32,7 @@ def test_prior_lowrank_factor(T, taus):
 
 
 @pytest.mark.parametrize("q,N,T,R", [(2, 20, 50, 5), (3, 7, 40, 4), (8, 100, 200, 3), (5, 3, 33, 3), (1, 5, 30, 2),
-                                       (3, 15, 60, 70)])
+                                       (3, 15, 60, 70), (10, 30, 250, 2), (12, 20, 64, 3), (9, 12, 70, 2)])
 def test_lowrank_posterior_matches_dense_path_and_oracle(q, N, T, R):
     from poisson_gpfa_b200 import kernels as kn
     ex, ys, params = problem(31 + q, q, N, T, R)

@@ -54,9 +54,13 @@ def launch_summaries(src, tag):
     shutil.copy(path, os.path.join(ROOT, "profiles", tag + "_launches_bench.csv"))
     ms = lambda x: x['gpu__time_duration.sum'] / 1e6
     by = lambda x: x.get('dram__bytes_read.sum', 0.0) + x.get('dram__bytes_write.sum', 0.0)
-    # one EM iteration = from after the selected inverse of iteration k-1 to the selected inverse of iteration k
-    big = [i for i, x in enumerate(L) if x['name'].startswith('lauum_tiles') and ms(x) > 5.0]
-    step = L[big[-2] + 1:big[-1] + 1]
+    piv = [i for i, x in enumerate(L) if x['name'].startswith('pivchol')]
+    lowrank = len(piv) >= 2
+    if lowrank:     # low-rank posterior pass: one EM iteration = from one prior factorisation (pivchol) to the next
+        step = L[piv[-2]:piv[-1]]
+    else:           # dense: from after the selected inverse of iteration k-1 to the selected inverse of iteration k
+        big = [i for i, x in enumerate(L) if x['name'].startswith('lauum_tiles') and ms(x) > 5.0]
+        step = L[big[-2] + 1:big[-1] + 1]
     agg = collections.OrderedDict()
     for x in step:
         a = agg.setdefault(x['name'], [0, 0.0, 0.0])
@@ -69,6 +73,11 @@ def launch_summaries(src, tag):
            "kernels": [{"kernel": k, "launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot, 4), "dram_bytes": v[2]}
                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]}
     json.dump(out, open(os.path.join(ROOT, "profiles", tag + "_launches_bench_step.json"), "w"), indent=1)
+    print("step: %d launches, %.1f ms serialised" % (len(step), tot))
+    for k in out["kernels"][:10]:
+        print("  %-36s x%-4d %8.2f ms  %5.1f%%" % (k["kernel"], k["launches"], k["ms"], 100 * k["share"]))
+    if lowrank:
+        return
     # the factorisation at the mode: the chol_diag + chol_panel launches right before the polish solve
     isolve = max(i for i, x in enumerate(L) if x['name'].startswith('chol_solve_kernel<double>'))
     j = isolve - 1
@@ -82,10 +91,43 @@ def launch_summaries(src, tag):
                "note": "operands: each panel CTA streams 2*j tiles of 32 KB; the L(j,:) row panel is shared by a slot's CTAs "
                        "through L2; outputs L (FP64) + FP32 mirror"}
     json.dump(traffic, open(os.path.join(ROOT, "profiles", tag + "_factor_traffic.json"), "w"), indent=1)
-    print("step: %d launches, %.1f ms serialised; factorisation: %d launches, %.1f GB" %
-          (len(step), tot, len(fac), traffic["dram_bytes_per_factorisation"] / 1e9))
-    for k in out["kernels"][:8]:
-        print("  %-36s x%-4d %8.2f ms  %5.1f%%" % (k["kernel"], k["launches"], k["ms"], 100 * k["share"]))
+    print("factorisation: %d launches, %.1f GB" % (len(fac), traffic["dram_bytes_per_factorisation"] / 1e9))
+
+
+def gemm_summary(src, tag):
+    """ncu --set full of the three gemm_nt launches of a warm E-step (capacitance, Yh, post_vsmGP)."""
+    rep = os.path.join(src, "prof_gemm_nt.ncu-rep")
+    if not os.path.exists(rep):
+        print("no", rep)
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, units = rows[0], rows[1]
+    extra = ["smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+    lines = ["# ncu --set full --clock-control none --import-source on -k regex:gemm_nt, tools/prof_lowrank.py (1024 trials, "
+             "q=8, T=200): capacitance blocks, Yh, post_vsmGP launches of a warm E-step"]
+    last = None
+    for r in rows[2:]:
+        lines.append("--- kernel %s grid %s" % (r[H.index("Kernel Name")][:40], r[H.index("Grid Size")]))
+        for m in PANEL_METRICS + extra:
+            if m in H:
+                lines.append("   %-80s %s %s" % (m, r[H.index(m)], units[H.index(m)]))
+        last = r
+    open(os.path.join(ROOT, "profiles", tag + "_ncu_gemm_nt.txt"), "w").write("\n".join(lines) + "\n")
+    def val(m, scale=1.0):
+        u = units[H.index(m)]
+        v = float(last[H.index(m)].replace(",", ""))
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0) * scale
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    json.dump({"what": "DRAM traffic of the post_vsmGP launch of gemm_nt_kernel (q x trials symmetric T x T x r products) from the "
+                       "ncu --set full capture of tools/prof_lowrank.py (profiles/%s_ncu_gemm_nt.txt, last launch), 1024 trials" % tag,
+               "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+               "tensor_pipe_active_pct": float(last[H.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]),
+               "grid": last[H.index("Grid Size")]},
+              open(os.path.join(ROOT, "profiles", tag + "_syrk_traffic.json"), "w"), indent=1)
+    print("\n".join(lines[-24:]))
 
 
 def panel_summary(src, tag, header):
@@ -114,4 +156,6 @@ if __name__ == "__main__":
                                         "(1024 trials, q=8, T=200, n=1600), current build")
     a = ap.parse_args()
     launch_summaries(a.src, a.tag)
-    panel_summary(a.src, a.tag, a.header)
+    gemm_summary(a.src, a.tag)
+    if os.environ.get("DENSE"):
+        panel_summary(a.src, a.tag, a.header)
