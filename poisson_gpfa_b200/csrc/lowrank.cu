@@ -132,15 +132,11 @@ __global__ void __launch_bounds__(128) lr_bins_kernel(const double *__restrict__
     for (int j = 0; j < Q; j++) {
 #pragma unroll
         for (int i = j + 1; i < Q; i++) {
-            // X(i,j) = -X(i,i) * sum_{k=j}^{i-1} L(i,k) X(k,j); rows are finished in increasing i, and row i's
-            // off-diagonal entries still hold L(i,k) for k > j while X(i,k') for k' < j is already final
+            // X(i,j) = -X(i,i) * sum_{k=j}^{i-1} L(i,k) X(k,j).  Columns are finished in increasing j and rows in increasing
+            // i: row i still holds L(i,k) for k >= j, column j already holds X(k,j) for j <= k < i, the diagonal holds 1/L
             double s = 0.0;
 #pragma unroll
-            for (int k = j; k < i; k++) {
-                const double lik = (k == j) ? a[i * (i + 1) / 2 + j] : a[i * (i + 1) / 2 + k];
-                const double xkj = (k == j) ? a[j * (j + 1) / 2 + j] : a[k * (k + 1) / 2 + j];
-                s += lik * xkj;
-            }
+            for (int k = j; k < i; k++) s += a[i * (i + 1) / 2 + k] * a[k * (k + 1) / 2 + j];     // L(i,k) X(k,j)
             a[i * (i + 1) / 2 + j] = -a[i * (i + 1) / 2 + i] * s;
         }
     }
