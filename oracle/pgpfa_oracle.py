@@ -142,6 +142,50 @@ def slice_cov(cov, q, T):
     return vsmGP, vsm
 
 
+def pivoted_cholesky(S, delta=1e-14):
+    """S ~= F F^T by greedy pivoted Cholesky, stopped when the largest residual diagonal entry is <= delta.
+    Restates csrc/lowrank.cu:pivchol_kernel (test infrastructure for the low-rank posterior pass)."""
+    T = S.shape[0]
+    dres = np.diag(S).astype(np.float64).copy()
+    F = np.zeros((T, T))
+    r = 0
+    while r < T:
+        j = int(np.argmax(dres))
+        if not dres[j] > delta:
+            break
+        col = (S[:, j] - F[:, :r] @ F[j, :r]) / np.sqrt(dres[j])
+        F[:, r] = col
+        dres = np.maximum(dres - col ** 2, 0.0)
+        dres[j] = -1.0
+        r += 1
+    return F[:, :r]
+
+
+def lowrank_posterior_slices(x, C, d, K, epsNoise=EPS_NOISE, delta=1e-14):
+    """post_vsmGP (T,T,q), post_vsm (T,q,q) of funs/inference.py:164-172 WITHOUT the qT x qT inverse: with
+    K_k - eps I = F_k F_k^T, P_t = (I + eps W_t)^-1 and Dt_t = W_t P_t,  Sigma = eps P + Y Y^T,
+    Y = P F L^-T,  L L^T = I + F^T Dt F  (Woodbury; the identity behind csrc/lowrank.cu)."""
+    q, T, _ = K.shape
+    W = nlp_W_struct(x, C, d)                                   # (T,q,q)
+    Fs = [pivoted_cholesky(K[k] - epsNoise * np.eye(T), delta) for k in range(q)]
+    off = np.concatenate([[0], np.cumsum([f.shape[1] for f in Fs])]).astype(int)
+    r = int(off[-1])
+    P = np.stack([np.linalg.inv(np.eye(q) + epsNoise * W[t]) for t in range(T)])
+    Dt = np.einsum('tkl,tlm->tkm', W, P)
+    G = np.eye(r)
+    for k in range(q):
+        for l in range(q):
+            G[off[k]:off[k + 1], off[l]:off[l + 1]] += Fs[k].T @ (Dt[:, k, l][:, None] * Fs[l])
+    Z = np.linalg.inv(np.linalg.cholesky(G))
+    Yh = [Fs[l] @ Z[:, off[l]:off[l + 1]].T for l in range(q)]  # (T,r) per latent
+    Y = [sum(P[:, k, l][:, None] * Yh[l] for l in range(q)) for k in range(q)]
+    vsmGP = np.zeros((T, T, q))
+    for k in range(q):
+        vsmGP[:, :, k] = Y[k] @ Y[k].T + np.diag(epsNoise * P[:, k, k])
+    vsm = epsNoise * P + np.einsum('ktc,ltc->tkl', np.stack(Y), np.stack(Y))
+    return vsmGP, vsm, r
+
+
 def _trial_list(experiment):
     return [np.asarray(tr['Y'], dtype=np.float64) for tr in experiment.data]
 

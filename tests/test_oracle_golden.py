@@ -188,3 +188,34 @@ def test_oracle_leave_one_out_matches_reference_golden():
     # are only good to ~3e-3; the exact-Newton fixed point is what is compared at 1e-8 on the GPU
     assert rel(pred, g['stock_y_pred_mode']) <= 5e-3
     assert abs(err - float(g['stock_pred_err_mode'])) <= 1e-3 * err
+
+
+@pytest.mark.parametrize("name,q,N,T", CASES)
+def test_lowrank_posterior_identity_matches_reference_covariances(name, q, N, T):
+    """Sigma = eps P + Y Y^T through the pivoted-Cholesky prior factor (the identity behind csrc/lowrank.cu, restated in
+    numpy) reproduces the covariance slices the UNMODIFIED reference returned (inv(hess) at its own optimum) and the
+    dense inverse of the oracle's Hessian, with an r x r system instead of qT x qT."""
+    g = load_golden(name)
+    ip = init_params(g)
+    K = po.make_K(ip['tau'], T, float(g['binSize']))
+    Kinv = np.stack([np.linalg.inv(K[k]) for k in range(q)])
+    for r_ in range(2):
+        x = np.asarray(g['it0_post_mean'][r_]).reshape(q, T)
+        vsmGP, vsm, r = po.lowrank_posterior_slices(x, ip['C'], ip['d'], K)
+        assert 0 < r < q * T
+        assert rel(vsm, g['it0_post_vsm'][r_]) <= 1e-9
+        assert rel(vsmGP, g['it0_post_vsmGP'][r_]) <= 1e-9
+        H = po.assemble_H(Kinv, po.nlp_W_struct(x, ip['C'], ip['d']))
+        vsmGP_d, vsm_d = po.slice_cov(np.linalg.inv(H), q, T)
+        assert rel(vsm, vsm_d) <= 1e-10 and rel(vsmGP, vsmGP_d) <= 1e-10
+
+
+def test_pivoted_cholesky_rank_follows_the_timescale():
+    K = po.make_K(np.array([0.02, 0.1, 0.5]), 120, 10.0)
+    ranks = []
+    for k in range(3):
+        S = K[k] - 0.001 * np.eye(120)
+        F = po.pivoted_cholesky(S)
+        assert np.abs(F @ F.T - S).max() <= 120 * 2e-14
+        ranks.append(F.shape[1])
+    assert ranks[0] > ranks[1] > ranks[2] and ranks[2] < 20
