@@ -46,23 +46,37 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.proc, self.lines, self.index = None, [], index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started before the warm-up so that nvidia-smi is already sampling (every 50 ms) when the timed region begins;
+        samples carry their arrival time and only those inside [begin(), end()] are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            threading.Thread(target=lambda: [self.lines.append((time.perf_counter(), l)) for l in self.proc.stdout],
+                             daemon=True).start()
         except Exception:
             self.proc = None
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        t0 = self.t0 if self.t0 is not None else -1e300
+        t1 = self.t1 if self.t1 is not None else 1e300
+        inside = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.03]
+        lines = inside if inside else [l for (_, l) in self.lines]     # region shorter than one sampling period
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in lines:
             p = [s.strip() for s in l.split(",")]
             try:
                 sm.append(float(p[0])); mx = float(p[1])
@@ -72,7 +86,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "samples_in_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 def cpu_sample(w, R_cpu, warm, timed):
@@ -159,6 +173,9 @@ def run_ours(args):
         return newp, est, lik, cd_it, det['nfev']
 
     params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
+    sampler = ClockSampler(dev_index)
+    if rank == 0:
+        sampler.start()                       # already sampling when the timed region begins
     x0, liks = None, []
     for _ in range(args.warmup):
         params, est, lik, _, _ = em_iteration(params, x0)
@@ -167,12 +184,10 @@ def run_ours(args):
 
     # ---------------- timed region: K steady-state EM iterations, device-resident inputs
     _lib.call("pgpfa_set_profiling", h, 1)
-    sampler = ClockSampler(dev_index)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.lib.pgpfa_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     newton_its, facts, cd_its, tau_evals, chord_its, fallback = [], 0, [], [], [], []
     for _ in range(args.steps):
@@ -184,6 +199,7 @@ def run_ours(args):
         chord_its.append(est.stats["pcg_newton_iters"]); fallback.append(est.stats["pcg_iters"])
     e1.record()
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.lib.pgpfa_launch_count() - launches0
@@ -334,15 +350,17 @@ def inference_experiment(Y_pin, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20 for our arm, 5 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trials", type=int, default=0, help="override the trial count (debug only)")
     ap.add_argument("--cpu-trials", type=int, default=2)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="timed loop only (for runs under ncu)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 20
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.warmup_ref = min(args.warmup, 1)
     if args.impl == "reference":
