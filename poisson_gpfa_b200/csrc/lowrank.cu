@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(128) lr_bins_kernel(const double *__restrict__
 // ---------------------------------------------------------------------------------------------
 // batched C = A B^T on the FP64 tensor pipe.  A (M x K) and B (N x K) row-major along K.  One launch covers a
 // table of problems (ragged blocks) times a batch.  CTA = 64 x 64 tile, 4 warps as 2 x 2 of 32 x 32; K in chunks of
-// 16 through double-buffered padded shared memory with register prefetch (as prior_apply_kernel / small_gemm_kernel).
+// 16 through a three-stage ring of padded shared-memory stages filled by cp.async (the k-stride of 20 doubles keeps
+// the 16 lanes of a half-warp on distinct 8-byte banks when they read their DMMA fragments).
 // ---------------------------------------------------------------------------------------------
 enum { GEMM_ADD_IDENTITY = 1, GEMM_SYMMETRIC = 2, GEMM_LOWER_ONLY = 4 };
 struct GemmProb {
