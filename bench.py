@@ -164,13 +164,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def em_iteration(params, x0):
-        est = trials.estep_laplace(params, x0=x0)
-        lik = trials.post_lik(est)
-        C, d, cost, cd_it, _ = trials.mstep_cd(params, est)
-        Psum = trials.pautosum(est)
-        tau, det = trials.mstep_tau(params, Psum)
-        newp = core.DeviceParams(C, d, tau, T, w["binSize"])
-        return newp, est, lik, cd_it, det['nfev']
+        newp, est, lik, info = trials.em_step(params, x0=x0)
+        return newp, est, lik, info["cd_iters"], info["tau_evals"]
 
     params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
     sampler = ClockSampler(dev_index)
@@ -185,6 +180,7 @@ def run_ours(args):
     # ---------------- timed region: K steady-state EM iterations, device-resident inputs
     _lib.call("pgpfa_set_profiling", h, 1)
     launches0 = _lib.lib.pgpfa_launch_count()
+    syncs0 = _lib.host_sync_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.begin()
@@ -203,6 +199,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.lib.pgpfa_launch_count() - launches0
+    host_syncs = _lib.host_sync_count() - syncs0
     prof_ms, prof_work, prof_cnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
     _lib.call("pgpfa_get_profile", h, ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_work, ctypes.c_void_p),
               ctypes.cast(prof_cnt, ctypes.c_void_p))
@@ -324,7 +321,8 @@ def run_ours(args):
                     "api": "inference.laplace + learning.updateParams with host numpy inputs/outputs each step"},
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
-                       "tau_evals": tau_evals, "inexact_newton_iters_per_step": chord_its, "pcg_iters_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce}}
+                       "tau_evals": tau_evals, "inexact_newton_iters_per_step": chord_its, "pcg_iters_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce,
+                       "host_syncs_per_step": host_syncs / args.steps}}
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:

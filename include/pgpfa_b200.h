@@ -9,7 +9,8 @@
  * Conventions: every array pointer is a DEVICE pointer (float64 unless stated, C-contiguous);
  * scalars by value; `stream` is a cudaStream_t passed as void*-compatible handle; every function
  * returns 0 on success or a PGPFA_ERR_* code and never throws.  The library owns no device memory:
- * callers pass workspaces sized by the *_workspace_bytes helpers.  One handle per device/thread.
+ * callers pass workspaces sized by the *_workspace_bytes helpers (a handle owns a few KB of pinned HOST memory for
+ * device-written progress words and table staging).  One handle per device/thread.
  *
  * Layouts: x[r][k][t] (latent-major, funs/inference.py:97 reshape), y[r][n][t], C[n][k], d[n],
  * K / Kinv [k][s][t], W[r][k*q+l][t], post_vsm[r][t][k][l] (= reference post_vsm[r], (T,q,q)),
@@ -29,7 +30,7 @@ typedef struct CUstream_st *cudaStream_t;
 
 typedef struct pgpfa_handle_s *pgpfa_handle_t;
 
-#define PGPFA_ABI_VERSION 1
+#define PGPFA_ABI_VERSION 2
 
 /* ---- lifecycle / errors -------------------------------------------------------------------- */
 int pgpfa_abi_version(void);
@@ -38,6 +39,16 @@ int pgpfa_destroy(pgpfa_handle_t h);
 const char *pgpfa_error_string(int code);
 const char *pgpfa_last_cuda_error(void);
 long long pgpfa_launch_count(void);                    /* kernels launched by this library so far */
+/* Host <-> device synchronisation made by the library's drivers on this handle so far: cudaStreamSynchronize calls
+ * plus blocking reads of a device-written progress word that had not arrived yet.  The iterative drivers (Newton /
+ * CG of funs/inference.py:119-126, the M-step optimisers of funs/learning.py:124-130, :283-288) run from device-side
+ * counters; pgpfa_set_loop_depth sets how many loop iterations they enqueue ahead of the last count the host has seen
+ * (default 4; 0 = wait for every count, i.e. a host-driven loop: same iterates bit for bit, used by the tests). */
+long long pgpfa_host_sync_count(pgpfa_handle_t h);
+/* throttle waits so far: the host wanted a count from `depth` iterations back that the device had not produced yet;
+ * unlike a synchronisation the device keeps working on the iterations queued behind it */
+long long pgpfa_throttle_wait_count(pgpfa_handle_t h);
+int pgpfa_set_loop_depth(pgpfa_handle_t h, int depth);
 /* in-stream CUDA-event profiling of the kernel families inside the drivers (bench.py roofline):
  * slots: 0 batched Cholesky, 1 triangular solves, 2 eval/prior/line-search, 3 triangular inverse,
  * 4 covariance slices; ms_out/work_out/count_out hold 8 entries each (work = algorithmic flops or bytes) */
@@ -179,15 +190,42 @@ int pgpfa_mstep_cd_stats(const double *y, const double *post_mean, const double 
 /* one accept/reject + Newton-step update per neuron; see poisson_gpfa_b200/learning.py.
  * prior: 0.5*prior_w*|theta-theta0|^2, or (prior_mat != NULL) 0.5*(theta-theta0)^T M_n (theta-theta0) with
  * per-neuron packed-upper (q+1)x(q+1) blocks prior_mat[b][n] */
+/* n_open: device int[4]; [0] receives the number of neurons still open, [1] the largest iter_index (>0) at which a
+ * neuron was still open */
 int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *prior_mat,
                           const double *theta0, double *theta_cur,
                           double *theta_try, double *fcur, double *step, double *alpha, double *slope, int *done,
-                          int first, double tol, int N, int q, int *n_open, cudaStream_t stream);
+                          int first, double tol, int N, int q, int *n_open, int iter_index, cudaStream_t stream);
+/* pgpfa_mstep_cd_stats as one iteration of a device-driven loop: exits at once when *n_open == 0 */
+int pgpfa_mstep_cd_stats_gated(const double *y, const double *post_mean, const double *vsm, const double *theta, int R,
+                               int q, int N, int T, double *stats, void *workspace, long long ws_bytes,
+                               const int *n_open, cudaStream_t stream);
+/* learnLTparams' optimiser loop (funs/learning.py:124-130, scipy TNC/BFGS there) as n_iters per-neuron Newton
+ * iterations enqueued without any host read: iteration = pgpfa_mstep_cd_stats_gated + pgpfa_mstep_cd_update on the
+ * caller's state arrays (theta_cur = theta_try = theta0, done = 0, n_open = 0 before first_iter = 1).  Iterations
+ * after convergence are empty launches.  Single rank; with trial sharding core.py runs the same two entry points
+ * around the all-reduce of `stats`. */
+int pgpfa_mstep_cd_solve(const double *y, const double *post_mean, const double *vsm, int R, int q, int N, int T,
+                         double inv_R, double prior_w, const double *prior_mat, const double *theta0,
+                         double *theta_cur, double *theta_try, double *fcur, double *step, double *alpha,
+                         double *slope, int *done, int *n_open, double *stats, int first_iter, int n_iters,
+                         double tol, void *workspace, long long ws_bytes, cudaStream_t stream);
 long long pgpfa_tau_eval_workspace_bytes(int q, int T);
 /* cost[k], grad[k] of MStepGPtimescaleCost(+WithPrior) at p[k]; prior_w = 1/step^2 or 0 */
 int pgpfa_tau_eval(const double *p, const double *PautoSum, double numTrials, int q, int T, double epsNoise,
                    double prior_w, const double *tau_old_sec, double binSize_ms, double *cost, double *grad,
                    void *workspace, long long ws_bytes, cudaStream_t stream);
+
+/* learnGPparams' optimiser loops (funs/learning.py:283-288; prior variant :819-825) for all latents on the device:
+ * rounds of m candidate points per latent -> one batched cost/gradient evaluation -> bracket / inverse-interpolation
+ * controller (csrc/tau_search.h).  first_round = 0 starts a search, a later call continues it on the same workspace.
+ * No host read: flags (device int[4]) = {latents still open, evaluations used, bracketed mask, walked-out mask};
+ * tau_new (q, s) and details (6,q) = {p, p0, grad, fun, fun0, grad0} are refreshed after every round.  m odd, 5..15. */
+long long pgpfa_tau_solve_workspace_bytes(int q, int T, int m);
+int pgpfa_mstep_tau_solve(const double *PautoSum, const double *tau_old_sec, double numTrials, int q, int T,
+                          double epsNoise, double prior_w, double binSize_ms, double xtol, int m, int first_round,
+                          int n_rounds, double *tau_new_sec, double *details, int *flags, void *workspace,
+                          long long ws_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -610,17 +610,41 @@ def tau_cost_prior_grad(p, precomp, binSize, oldTau, step, epsNoise=EPS_NOISE):
     return tau_cost_grad(p, precomp, epsNoise) + (tau - oldTau) / step ** 2
 
 
-def learn_tau(params, infRes, binSize, gtol=1e-8):
-    """funs/learning.py:257-293 (scipy default method = BFGS, gtol=1e-8)."""
+def _polish_root(fun_grad, p, width=1e-3):
+    """Zero of a scalar gradient near p: bracket + Brent to the last ulp.  scipy's BFGS ends with 'precision loss' in its
+    line search up to |g| ~ 1e-5 away from the stationary point on some hosts (measured: p off by 1e-7 on the GPU boxes'
+    CPUs, 1e-14 elsewhere, same inputs); the float64 root itself is the exact stationary point to ~1e-13 in p
+    (tests/test_tau_search_host.py, 40-digit arithmetic).  Used only in tight (fixed-point parity) mode."""
+    g = lambda v: float(np.ravel(fun_grad(v))[0])
+    a, b = p - width, p + width
+    ga, gb = g(a), g(b)
+    for _ in range(8):
+        if ga * gb < 0:
+            break
+        width *= 4
+        a, b = p - width, p + width
+        ga, gb = g(a), g(b)
+    if ga * gb >= 0:
+        return p
+    return sopt.brentq(g, a, b, xtol=1e-15, rtol=1e-15)
+
+
+def learn_tau(params, infRes, binSize, gtol=1e-8, polish=None):
+    """funs/learning.py:257-293 (scipy default method = BFGS, gtol=1e-8).  polish (default: when gtol < 1e-8, i.e. the
+    tight mode of the parity tests): refine BFGS's end point to the zero of the same gradient function."""
     q = infRes['post_mean'][0].shape[0]
     oldTau = np.ravel(params['tau']) * 1000 / binSize
     pre = make_precomp(infRes)
     new = np.zeros(q)
     details = []
+    polish = (gtol < 1e-8) if polish is None else polish
     for k in range(q):
         p0 = np.log(1 / oldTau[k] ** 2)
         out = sopt.minimize(tau_cost, p0, args=(pre[k], EPS_NOISE), jac=tau_cost_grad,
                             options={'disp': False, 'gtol': gtol})
+        if polish:
+            out.x_bfgs = out.x.copy()
+            out.x = np.array([_polish_root(lambda v: tau_cost_grad(v, pre[k]), float(out.x[0]))])
         details.append(out)
         new[k] = (1 / np.exp(out.x[0])) ** 0.5
     return new * binSize / 1000, details

@@ -23,6 +23,9 @@ SIGNATURES = {
     "pgpfa_error_string": (ctypes.c_char_p, [c_int]),
     "pgpfa_last_cuda_error": (ctypes.c_char_p, []),
     "pgpfa_launch_count": (c_ll, []),
+    "pgpfa_host_sync_count": (c_ll, [c_void_p]),
+    "pgpfa_set_loop_depth": (c_int, [c_void_p, c_int]),
+    "pgpfa_throttle_wait_count": (c_ll, [c_void_p]),
     "pgpfa_stream_wait_means": (c_int, [c_void_p, c_void_p]),
     "pgpfa_prior_lowrank": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P, P, P]),
     "pgpfa_laplace_solve_lowrank": (c_int, [c_void_p, P, P, P, P, P, P, P, c_dbl, P, c_int, c_int, c_int, c_int, c_dbl, c_int,
@@ -66,7 +69,13 @@ SIGNATURES = {
     "pgpfa_mstep_cd_nstats": (c_int, [c_int]),
     "pgpfa_mstep_cd_workspace_bytes": (c_ll, [c_int, c_int]),
     "pgpfa_mstep_cd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_ll, P]),
-    "pgpfa_mstep_cd_update": (c_int, [P, c_dbl, c_dbl, P, P, P, P, P, P, P, P, P, c_int, c_dbl, c_int, c_int, P, P]),
+    "pgpfa_mstep_cd_update": (c_int, [P, c_dbl, c_dbl, P, P, P, P, P, P, P, P, P, c_int, c_dbl, c_int, c_int, P, c_int, P]),
+    "pgpfa_mstep_cd_stats_gated": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_ll, P, P]),
+    "pgpfa_mstep_cd_solve": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_dbl, c_dbl, P, P, P, P, P, P, P, P, P, P, P,
+                                     c_int, c_int, c_dbl, P, c_ll, P]),
+    "pgpfa_tau_solve_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
+    "pgpfa_mstep_tau_solve": (c_int, [P, P, c_dbl, c_int, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, P, P, P,
+                                      P, c_ll, P]),
     "pgpfa_tau_eval_workspace_bytes": (c_ll, [c_int, c_int]),
     "pgpfa_tau_eval": (c_int, [P, P, c_dbl, c_int, c_int, c_dbl, c_dbl, P, c_dbl, P, P, P, c_ll, P]),
 }
@@ -131,6 +140,21 @@ def call(name, *args, allow=()):
     if rc != 0 and rc not in allow:
         raise PgpfaError(rc, name)
     return rc
+
+
+# host reads of device results made by the Python layer (each one waits for the stream): bench.py reports them per step
+host_reads = [0]
+
+
+def to_host(t):
+    """Device tensor -> numpy, counted as one host synchronisation."""
+    host_reads[0] += 1
+    return t.detach().cpu().numpy()
+
+
+def host_sync_count():
+    """Synchronisations so far: inside the library's drivers (this device's handle) + host reads of the Python layer."""
+    return int(lib.pgpfa_host_sync_count(handle())) + host_reads[0]
 
 
 def dev_f64(a):

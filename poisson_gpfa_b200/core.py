@@ -33,52 +33,88 @@ def _side_stream():
     return _side_streams[dev]
 
 
+def read_packed(tensors):
+    """ONE device -> host copy (one synchronisation) for a list of small device tensors; returns float64 numpy arrays
+    of the original shapes.  Integer tensors are converted (exact below 2^53)."""
+    flat = torch.cat([t.detach().reshape(-1).to(torch.float64) for t in tensors])
+    host = _lib.to_host(flat)
+    out, o = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append(host[o:o + n].reshape(tuple(t.shape)))
+        o += n
+    return out
+
+
 class DeviceParams:
-    """C (N,q), d (N), tau (q, seconds) on the device plus the derived prior blocks."""
+    """C (N,q), d (N), tau (q, seconds) on the device plus the derived prior blocks.
+
+    ``prepare()`` only ENQUEUES the prior construction (K, K^-1 by q independent T x T Cholesky inverses — the
+    reference inverts the block-diagonal qT x qT K_big with one dense LU, funs/inference.py:82 — and the pivoted-Cholesky
+    low-rank factor); the two small results the host needs (is K positive definite, the ranks) are read either together
+    with other flags (``pending()`` / ``resolve()``, used by the device-resident EM step) or lazily on first use."""
 
     def __init__(self, C, d, tau, T, binSize):
         self.C = _lib.dev_f64(C)
         self.d = _lib.dev_f64(np.ravel(d) if not isinstance(d, torch.Tensor) else d.reshape(-1))
         self.tau = _lib.dev_f64(np.ravel(tau) if not isinstance(tau, torch.Tensor) else tau.reshape(-1))
         self.T, self.binSize = int(T), float(binSize)
-        self._K = self._Kinv = self._logdetK = None
-        self._lowrank = False
+        self._K = self._Kinv = self._logdetK = self._Kinfo = None
+        self._lr_dev = None          # (F, Ft, ranks on the device)
+        self._resolved = False
+        self._lowrank = None
+        self._use_lr = os.environ.get("PGPFA_LOWRANK", "1") != "0"
 
     @property
     def q(self):
         return self.C.shape[1]
 
-    @property
-    def K(self):
+    def prepare(self):
         if self._K is None:
             self._K = kn.make_K(self.tau, self.T, self.binSize, EPS_NOISE)
-        return self._K
+            self._Kinv, self._logdetK, self._Kinfo = kn.spd_inverse(self._K)
+            if self._use_lr:
+                self._lr_dev = kn.prior_lowrank_async(self._K, EPS_NOISE, LOWRANK_DELTA)
+        return self
+
+    def pending(self):
+        """Small device tensors whose host values ``resolve`` needs (one packed read for all of them)."""
+        self.prepare()
+        return [self._Kinfo] + ([self._lr_dev[2]] if self._lr_dev is not None else [])
+
+    def resolve(self, host_vals=None):
+        if self._resolved:
+            return self
+        if host_vals is None:
+            host_vals = read_packed(self.pending())
+        if np.abs(host_vals[0]).max() != 0:
+            raise FloatingPointError("GP prior covariance K is not positive definite (tau=%s)" % self.tau.tolist())
+        if self._lr_dev is not None:
+            ranks = [int(v) for v in host_vals[1]]
+            # the low-rank pass only when the prior's numerical rank is small (sum of ranks <= qT/2); short timescales
+            # make the dense tiled path the cheaper one
+            if 0 < sum(ranks) <= (self.q * self.T) // 2:
+                self._lowrank = (self._lr_dev[0], self._lr_dev[1], ranks, EPS_NOISE)
+        self._resolved = True
+        return self
+
+    @property
+    def K(self):
+        return self.prepare()._K
 
     @property
     def Kinv(self):
-        """K^-1 per latent: q independent T x T Cholesky inverses (the reference inverts the block-diagonal
-        qT x qT K_big with one dense LU, funs/inference.py:82)."""
-        if self._Kinv is None:
-            self._Kinv, self._logdetK, info = kn.spd_inverse(self.K)
-            if int(info.abs().max()) != 0:
-                raise FloatingPointError("GP prior covariance K is not positive definite (tau=%s)" % self.tau.tolist())
-        return self._Kinv
+        return self.resolve()._Kinv
 
     @property
     def lowrank(self):
         """(F, Ft, ranks, eps) with K_k - eps I = F_k F_k^T (pivoted Cholesky, residual <= 1e-14), or None when the
-        prior's numerical rank is not small (sum of ranks > qT/2: short timescales) and the dense path is the cheaper
-        one.  PGPFA_LOWRANK=0 disables it."""
-        if self._lowrank is False:
-            self._lowrank = None
-            if os.environ.get("PGPFA_LOWRANK", "1") != "0":
-                F, Ft, ranks = kn.prior_lowrank(self.K, EPS_NOISE, LOWRANK_DELTA)
-                if 0 < sum(ranks) <= (self.q * self.T) // 2:
-                    self._lowrank = (F, Ft, ranks, EPS_NOISE)
-        return self._lowrank
+        prior's numerical rank is not small.  PGPFA_LOWRANK=0 disables it."""
+        return self.resolve()._lowrank
 
     def to_numpy_dict(self):
-        return {'C': self.C.cpu().numpy(), 'd': self.d.cpu().numpy(), 'tau': self.tau.cpu().numpy()}
+        C, d, tau = read_packed([self.C, self.d, self.tau])
+        return {'C': C, 'd': d, 'tau': tau}
 
     @property
     def theta(self):
@@ -88,20 +124,121 @@ class DeviceParams:
 class EStepResult:
     """Posterior statistics of one E-step, device resident (layouts of include/pgpfa_b200.h)."""
 
-    def __init__(self, x, f, vsm, vsmGP, niter, stats, params, trials):
+    def __init__(self, x, f, vsm, vsmGP, niter, stats, params, trials, info=None):
         self.x, self.f, self.vsm, self.vsmGP = x, f, vsm, vsmGP
-        self.niter, self.stats = niter, stats
+        self.niter, self.stats, self.info = niter, stats, info
         self.params, self.trials = params, trials
         self.side = None      # stream on which x / f / vsm are complete while vsmGP may still be in flight on the main one
+        self._checked = False
 
     def means_stream(self):
         """Context in which work that needs only x, f and vsm runs: the side stream if the E-step left one."""
         return torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
 
+    def flags(self):
+        """Device tensor [sum_r f_r, 1 if a posterior Hessian of this shard was not positive definite, 1 if the Newton
+        iteration limit was reached] (enqueued on the means stream).  It is summed over ranks together with the
+        objective, so every rank sees a failure of any rank at the same read."""
+        with self.means_stream():
+            fl = torch.zeros(3, dtype=torch.float64, device="cuda")
+            if self.f is not None and self.f.numel():
+                fl[0] = self.f.sum()
+                if self.info is not None:
+                    fl[1] = (self.info != 0).any().to(torch.float64)
+            if self.stats and self.stats.get("not_converged", 0) > 0:
+                fl[2] = 1.0
+        return fl
+
+    @staticmethod
+    def raise_on(flags_host, what="Laplace"):
+        fsum, notpd, notconv = (float(v) for v in flags_host[:3])
+        if notpd != 0:
+            raise FloatingPointError("%s E-step: posterior Hessian / precision not positive definite for at least one trial"
+                                     % what)
+        if notconv != 0:
+            raise RuntimeError("%s E-step: iteration limit reached before every trial converged" % what)
+        if not np.isfinite(fsum):
+            raise FloatingPointError("%s E-step: non-finite objective (rate overflow?)" % what)
+
+
+class CdSolve:
+    """State of a C,d Newton solve in flight on the device (DeviceTrials.mstep_cd_async)."""
+
+    def __init__(self, trials, est, q, N):
+        self.trials, self.est, self.q, self.N = trials, est, q, N
+        self.issued = 0
+        self.hess = None
+        self.fsum = None
+
+    def pending(self):
+        """[n_open (int[4]), sum of the per-neuron costs, (objective sum, E-step error code)]"""
+        with self.est.means_stream():
+            out = [self.n_open, self.fcur.sum().reshape(1), self.extra]
+        return out
+
+    def finish(self, host_vals=None, max_iter=100):
+        """Host side of the solve: read the flags (unless given), run more iterations while neurons are open (rare: the
+        blind schedule covers the usual 3-4), hand back (C, d, cost, iterations, hess)."""
+        t = self.trials
+        if host_vals is None:
+            pend = self.pending()          # enqueued on the solve's stream: join AFTER it, then read on the caller's
+            self.join()
+            host_vals = read_packed(pend)
+        n_open, cost, extra = host_vals
+        while n_open[0] > 0 and self.issued < max_iter:
+            with self.est.means_stream():
+                t._cd_iterate(self, 1)
+            pend = self.pending()
+            self.join()
+            n_open, cost, extra = read_packed(pend)
+        q = self.q
+        with self.est.means_stream():
+            C_new, d_new = self.th_cur[:, :q].contiguous(), self.th_cur[:, q].contiguous()
+        self.join((C_new, d_new))
+        self.extra_host = extra
+        its = int(n_open[1]) if not self.one_step else 1
+        return C_new, d_new, float(cost[0]), its, self.hess
+
+    def join(self, tensors=()):
+        """Order the caller's stream after the solve's (side) stream."""
+        side = self.est.side
+        if side is not None:
+            self.main.wait_stream(side)
+            for x in tensors:
+                x.record_stream(self.main)
+
+
+class TauSolve:
+    """State of a timescale search in flight on the device (DeviceTrials.mstep_tau_async)."""
+
+    def pending(self):
+        return [self.flags]
+
+    def finish(self, host_vals=None, max_rounds=14):
+        t = self.trials
+        if host_vals is None:
+            host_vals = read_packed(self.pending())
+        flags = host_vals[0]
+        while flags[0] > 0 and self.rounds < max_rounds + 1:
+            t._tau_rounds(self, 1)
+            flags = read_packed(self.pending())[0]
+        self.flags_host = flags
+        return self.tau
+
+    def details(self):
+        """Host dictionary of the search (one read): p, p0, grad, fun, fun0, grad0, nfev, bracketed."""
+        det, = read_packed([self.det])
+        fl = self.flags_host
+        q = det.shape[1]
+        br = np.array([(int(fl[2]) >> k) & 1 for k in range(q)], dtype=bool)
+        return {'p': det[0], 'p0': det[1], 'grad': det[2], 'fun': det[3], 'fun0': det[4], 'grad0': det[5],
+                'nfev': int(fl[1]), 'bracketed': br}
+
 
 class DeviceTrials:
     """One rank's trials: y (R_local, N, T) float64 in HBM (counts are promoted to float64 exactly as the
-    reference does on use; s_y = 8 bytes in the roofline byte counts)."""
+    reference does on use; s_y = 8 bytes in the roofline byte counts).  R_local may be 0 (a mini-batch smaller than
+    the world): such a rank launches nothing, contributes zero statistics and still joins every collective."""
 
     def __init__(self, y, binSize, reducer=None, R_total=None, offset=0):
         self.y = y if isinstance(y, torch.Tensor) else _lib.dev_f64(y)
@@ -117,8 +254,8 @@ class DeviceTrials:
 
     def _means_stream(self):
         """High-priority stream ordered after the point of the last Laplace solve where the posterior means and
-        time-diagonal covariances are final (pgpfa_stream_wait_means): the info check, the objective and the C,d
-        M-step run there, underneath the selected-inverse kernel that is still producing post_vsmGP."""
+        time-diagonal covariances are final (pgpfa_stream_wait_means): the objective and the whole C,d M-step run
+        there, underneath the batched GEMM that is still producing post_vsmGP."""
         if os.environ.get("PGPFA_SIDE_STREAM", "1") == "0":      # debugging switch: everything on the caller's stream
             return None
         side = _side_stream()
@@ -127,8 +264,16 @@ class DeviceTrials:
 
     # ------------------------------------------------------------------ E-step
     def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True):
+        """Batched Laplace E-step.  `tol` bounds the last Newton step (relative, inf-norm); the returned mode is one
+        polishing Newton step closer (~1e-13 measured), the covariances are those at the point before that step
+        (within ~4e-11 of the converged ones at tol = 1e-8, tools/parity_report.py)."""
         R, N, T = self.y.shape
         q = params.q
+        if R == 0:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float64, device="cuda")
+            return EStepResult(z(0, q, T), z(0), z(0, T, q, q), z(0, q, T, T) if want_vsmGP else None,
+                               torch.zeros(0, dtype=torch.int32, device="cuda"), {"not_converged": 0, "lowrank_r": 0}, params,
+                               self, info=torch.zeros(0, dtype=torch.int32, device="cuda"))
         if self._lap_ws is None or self._lap_ws[0] != (R, q, T):
             full = _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, R)
             free, _ = torch.cuda.mem_get_info()
@@ -138,206 +283,213 @@ class DeviceTrials:
         res = kn.laplace_solve(self.y, params.C, params.d, params.Kinv, x0=x0, tol=tol, max_newton=max_newton,
                                want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton,
                                lowrank=params.lowrank)
-        est = EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
+        est = EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self, info=res.info)
         est.side = self._means_stream()
-        with est.means_stream():
-            if int(res.info.abs().max()) != 0:
-                raise FloatingPointError("posterior Hessian not positive definite for %d trial(s)"
-                                         % int((res.info != 0).sum()))
         return est
 
     def estep_variational(self, params, lam0=None, tol=1e-10, max_iter=300, want_vsmGP=True):
         """Dual variational E-step (funs/inference.py:259-432): the stationary point of the dual for every
         trial of the shard.  Returns (EStepResult with the VARIATIONAL mean/covariance slices, lam (R,N,T),
         dual values (R))."""
+        if self.R == 0:
+            est = self.estep_laplace(params)
+            est.lam = torch.zeros(0, self.N, self.T, dtype=torch.float64, device="cuda")
+            est.dual = torch.zeros(0, dtype=torch.float64, device="cuda")
+            return est
         res = kn.dualvi_solve(self.y, params.C, params.d, params.K, params.Kinv, lam0=lam0, tol=tol,
                               max_iter=max_iter, want_vsmGP=want_vsmGP)
-        if int(res.info.abs().max()) != 0:
-            raise FloatingPointError("variational posterior precision not positive definite")
-        if res.rc != 0:
-            raise RuntimeError("dual variational fixed point: %d trial(s) not converged in %d sweeps"
-                               % (res.stats["not_converged"], max_iter))
-        est = EStepResult(res.mean, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self)
+        res.stats["not_converged_sweeps"] = res.stats["not_converged"]
+        est = EStepResult(res.mean, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self, info=res.info)
         est.lam, est.dual = res.lam, res.D
         return est
 
-    def post_lik(self, est):
-        """-mean_r L(x_r*) over ALL trials (funs/inference.py:175,183)."""
-        with est.means_stream():
-            return -self.reducer.sum_scalar(float(est.f.sum())) / self.R_total
+    def post_lik(self, est, what="Laplace"):
+        """-mean_r L(x_r*) over ALL trials (funs/inference.py:175,183).  One packed read: the objective sum travels with
+        the E-step's error code through the same all-reduce, so a failure on any rank raises on every rank."""
+        fl = est.flags()
+        with est.means_stream():           # the read synchronises the stream the flags were produced on
+            fl = self.reducer.sum_tensor(fl)
+            fl = _lib.to_host(fl)
+        EStepResult.raise_on(fl, what)
+        est._checked = True
+        return -float(fl[0]) / self.R_total
 
     # ------------------------------------------------------------------ M-step C,d
-    def mstep_cd(self, params, est, prior_w=0.0, tol=1e-10, max_iter=100, one_step=False, step_size=1.0,
-                 prior_mat=None):
-        """Per-neuron damped Newton on MStepObservationCost (+ 0.5*prior_w*|theta-theta_old|^2).
-        Returns (C, d, cost, iterations).  `one_step`: a single (scaled) Newton step from the old
-        parameters, the 'grad' online rule of funs/learning.py:884-891 with the analytic Hessian."""
+    def _cd_iterate(self, cd, n_iters):
+        """Enqueue n_iters Newton iterations of a C,d solve (no host read)."""
+        est = cd.est
+        N, q = cd.N, cd.q
+        inv_R = 1.0 / self.R_total
+        NS = kn.mstep_cd_nstats(q)
+        single = not (self.reducer.active and self.reducer.world_size > 1)
+        if single and not cd.first_pending_extra and self.R > 0:
+            call("pgpfa_mstep_cd_solve", ptr(self.y), ptr(est.x), ptr(est.vsm), self.R, q, N, self.T, inv_R,
+                 float(cd.prior_w), ptr(cd.prior_mat), ptr(cd.theta0), ptr(cd.th_cur), ptr(cd.th_try), ptr(cd.fcur),
+                 ptr(cd.step), ptr(cd.alpha), ptr(cd.slope), ptr(cd.done), ptr(cd.n_open), ptr(cd.stats), cd.issued + 1,
+                 int(n_iters), float(cd.tol), ptr(self._cd_ws[1]), self._cd_ws[1].numel(), stream())
+            cd.issued += n_iters
+            return
+        for _ in range(n_iters):
+            it = cd.issued + 1
+            gate = None if it == 1 else cd.n_open
+            call("pgpfa_mstep_cd_stats_gated", ptr(self.y), ptr(est.x), ptr(est.vsm), ptr(cd.th_try), self.R, q, N, self.T,
+                 ptr(cd.stats), ptr(self._cd_ws[1]), self._cd_ws[1].numel(), ptr(gate), stream())
+            if cd.first_pending_extra:                    # the objective sum and the E-step error flags ride along
+                cd.stats[NS:NS + 3, 0] = est.flags()
+            self.reducer.sum_tensor(cd.stats)
+            if cd.first_pending_extra:
+                cd.extra = cd.stats[NS:NS + 3, 0].clone()
+                cd.first_pending_extra = False
+            call("pgpfa_mstep_cd_update", ptr(cd.stats), inv_R, float(cd.prior_w), ptr(cd.prior_mat), ptr(cd.theta0),
+                 ptr(cd.th_cur), ptr(cd.th_try), ptr(cd.fcur), ptr(cd.step), ptr(cd.alpha), ptr(cd.slope), ptr(cd.done),
+                 1 if it == 1 else 0, float(cd.tol), N, q, ptr(cd.n_open), it, stream())
+            cd.issued += 1
+
+    def mstep_cd_async(self, params, est, prior_w=0.0, tol=1e-10, one_step=False, step_size=1.0, prior_mat=None,
+                       n_blind=4):
+        """Per-neuron damped Newton on MStepObservationCost (+ prior term), enqueued without host reads:
+        `n_blind` iterations (the usual solve takes 3-4; iterations after convergence are empty launches), the rest —
+        if any neuron is still open — in CdSolve.finish().  With trial sharding the per-neuron statistics are
+        all-reduced once per iteration; the first reduction also carries the E-step's objective sum and error code."""
         main = torch.cuda.current_stream()
+        N, q = params.C.shape
+        P = q + 1
+        cd = CdSolve(self, est, q, N)
+        cd.main, cd.one_step = main, one_step
+        cd.prior_w, cd.prior_mat, cd.tol = prior_w, prior_mat, (0.0 if one_step else tol)
         with est.means_stream():
-            N, q = params.C.shape
-            P = q + 1
-            theta0 = params.theta
-            th_cur, th_try = theta0.clone(), theta0.clone()
-            fcur, alpha, slope = empty(N), empty(N), empty(N)
-            step = empty(N, P)
-            done = torch.zeros(N, dtype=torch.int32, device="cuda")
-            n_open = torch.zeros(1, dtype=torch.int32, device="cuda")
+            cd.theta0 = params.theta
+            cd.th_cur, cd.th_try = cd.theta0.clone(), cd.theta0.clone()
+            cd.fcur, cd.alpha, cd.slope = empty(N), empty(N), empty(N)
+            cd.step = empty(N, P)
+            cd.done = torch.zeros(N, dtype=torch.int32, device="cuda")
+            cd.n_open = torch.zeros(4, dtype=torch.int32, device="cuda")
+            # per-neuron statistics + 3 extra rows whose first column carries the E-step flags through the first all-reduce
+            cd.stats = torch.zeros(kn.mstep_cd_nstats(q) + 3, N, dtype=torch.float64, device="cuda")
             if self._cd_ws is None or self._cd_ws[0] != (q, N):
                 self._cd_ws = ((q, N), _lib.workspace(_lib.lib.pgpfa_mstep_cd_workspace_bytes(q, N)))
-            inv_R = 1.0 / self.R_total
-            it = 0
-            hess = None
-            for it in range(1, max_iter + 1):
-                stats = kn.mstep_cd_stats(self.y, est.x, est.vsm, th_try, ws=self._cd_ws[1])
-                stats = self.reducer.sum_tensor(stats)
-                if one_step:
-                    hess = stats
-                    call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
-                         ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1, 0.0, N, q, ptr(n_open),
-                         stream())
-                    th_cur = kn.emap("axpy", theta0, step, step_size)
-                    break
-                call("pgpfa_mstep_cd_update", ptr(stats), inv_R, float(prior_w), ptr(prior_mat), ptr(theta0), ptr(th_cur),
-                     ptr(th_try), ptr(fcur), ptr(step), ptr(alpha), ptr(slope), ptr(done), 1 if it == 1 else 0, float(tol),
-                     N, q, ptr(n_open), stream())
-                if int(n_open.item()) == 0:
-                    break
-            cost = float(fcur.sum())
-            C_new, d_new = th_cur[:, :q].contiguous(), th_cur[:, q].contiguous()
-        if est.side is not None:                 # results were produced on the side stream: order the main one after it
-            main.wait_stream(est.side)
-            for t in (C_new, d_new) + ((hess,) if hess is not None else ()):
-                t.record_stream(main)
-        return C_new, d_new, cost, it, hess
+            multi = self.reducer.active and self.reducer.world_size > 1
+            cd.first_pending_extra = bool(multi)
+            if not multi:
+                cd.extra = est.flags()
+            if one_step:
+                # 'grad' online rule (funs/learning.py:884-891 with the analytic Hessian): one scaled Newton step
+                self._cd_iterate_one_step(cd, step_size)
+            else:
+                self._cd_iterate(cd, n_blind)
+        return cd
+
+    def _cd_iterate_one_step(self, cd, step_size):
+        est = cd.est
+        N, q = cd.N, cd.q
+        NS = kn.mstep_cd_nstats(q)
+        inv_R = 1.0 / self.R_total
+        call("pgpfa_mstep_cd_stats_gated", ptr(self.y), ptr(est.x), ptr(est.vsm), ptr(cd.th_try), self.R, q, N, self.T,
+             ptr(cd.stats), ptr(self._cd_ws[1]), self._cd_ws[1].numel(), None, stream())
+        if cd.first_pending_extra:
+            cd.stats[NS:NS + 3, 0] = est.flags()
+        self.reducer.sum_tensor(cd.stats)
+        if cd.first_pending_extra:
+            cd.extra = cd.stats[NS:NS + 3, 0].clone()
+            cd.first_pending_extra = False
+        cd.hess = cd.stats[:NS].clone()
+        call("pgpfa_mstep_cd_update", ptr(cd.stats), inv_R, float(cd.prior_w), ptr(cd.prior_mat), ptr(cd.theta0),
+             ptr(cd.th_cur), ptr(cd.th_try), ptr(cd.fcur), ptr(cd.step), ptr(cd.alpha), ptr(cd.slope), ptr(cd.done), 1, 0.0,
+             N, q, ptr(cd.n_open), 1, stream())
+        cd.th_cur = kn.emap("axpy", cd.theta0, cd.step, step_size)
+        cd.n_open.zero_()
+        cd.issued = 1
+
+    def mstep_cd(self, params, est, prior_w=0.0, tol=1e-10, max_iter=100, one_step=False, step_size=1.0,
+                 prior_mat=None):
+        """Returns (C, d, cost, iterations, hess) — see mstep_cd_async."""
+        cd = self.mstep_cd_async(params, est, prior_w=prior_w, tol=tol, one_step=one_step, step_size=step_size,
+                                 prior_mat=prior_mat, n_blind=min(4, max_iter))
+        out = cd.finish(max_iter=max_iter)
+        if not est._checked:
+            EStepResult.raise_on(cd.extra_host)
+            est._checked = True
+        return out
 
     def cd_cost_grad(self, theta, est):
         """(cost, grad (N,q+1)) of MStepObservationCost at theta, normalised by the global trial count."""
         q = theta.shape[1] - 1
-        stats = self.reducer.sum_tensor(kn.mstep_cd_stats(self.y, est.x, est.vsm, theta))
-        return float(stats[0].sum()) / self.R_total, (stats[1:q + 2].T / self.R_total).contiguous(), stats
+        if self.R > 0:
+            stats = kn.mstep_cd_stats(self.y, est.x, est.vsm, theta)
+        else:
+            stats = torch.zeros(kn.mstep_cd_nstats(q), self.N, dtype=torch.float64, device="cuda")
+        stats = self.reducer.sum_tensor(stats)
+        return float(_lib.to_host(stats[0].sum())) / self.R_total, (stats[1:q + 2].T / self.R_total).contiguous(), stats
 
     # ------------------------------------------------------------------ M-step tau
     def pautosum(self, est):
-        P = kn.pautosum(est.vsmGP, est.x)
+        if self.R > 0:
+            P = kn.pautosum(est.vsmGP, est.x)
+        else:
+            P = torch.zeros(est.params.q, self.T, self.T, dtype=torch.float64, device="cuda")
         return self.reducer.sum_tensor(P)
 
-    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, xtol=1e-10, max_rounds=14, ncand=9):
-        """q independent scalar minimisations over p = log(1/tau_bins^2) (funs/learning.py:257-293, :771-830).
-        The reference hands each to scipy (BFGS / TNC) from p0 = the old tau; the result is the first zero of
-        the gradient in the descent direction from p0.  Here all latents advance in lock-step and every device
-        launch evaluates `ncand` candidate points per latent (the T x T factorisations are latency-bound, so
-        candidates are free): round 1 brackets the sign change of the gradient around p0, later rounds place
-        the candidates around the inverse-cubic interpolant of the bracket's neighbours (error ~ width^4), so
-        3-4 launches reach |dp| < 2e-11.  Returns (tau_seconds (q), details)."""
-        q, T = params.q, self.T
-        R = float(self.R_total if numTrials is None else numTrials)
+    def _tau_rounds(self, ts, n_rounds):
+        call("pgpfa_mstep_tau_solve", ptr(ts.Psum), ptr(ts.tau_old), float(ts.R), ts.q, self.T, EPS_NOISE, float(ts.pw),
+             self.binSize, float(ts.xtol), ts.m, ts.rounds, int(n_rounds), ptr(ts.tau), ptr(ts.det), ptr(ts.flags),
+             ptr(self._tau_ws[1]), self._tau_ws[1].numel(), stream())
+        ts.rounds += n_rounds
+
+    def mstep_tau_async(self, params, Psum, numTrials=None, prior_step=None, xtol=1e-10, ncand=9, n_blind=3):
+        """q independent scalar minimisations over p = log(1/tau_bins^2) (funs/learning.py:257-293, :771-830), searched on
+        the device (pgpfa_mstep_tau_solve, csrc/tau_search.h): every round evaluates `ncand` candidate points per latent
+        in one batched launch sequence (the T x T factorisations are latency-bound, so candidates are free) and a
+        controller kernel brackets the sign change of the gradient / refines it by inverse interpolation.  `n_blind`
+        rounds are enqueued without host reads (the usual search takes 3); TauSolve.finish() adds rounds if a latent is
+        still open.  Every rank runs the identical search on the all-reduced PautoSum."""
+        q = params.q
         m = int(ncand)
-        key = (q, T, m)
+        ts = TauSolve()
+        ts.trials, ts.q, ts.m, ts.xtol = self, q, m, xtol
+        ts.R = float(self.R_total if numTrials is None else numTrials)
+        ts.pw = 0.0 if prior_step is None else 1.0 / float(prior_step) ** 2
+        key = (q, self.T, m)
         if self._tau_ws is None or self._tau_ws[0] != key:
-            self._tau_ws = (key, _lib.workspace(_lib.lib.pgpfa_tau_eval_workspace_bytes(q * m, T)))
-        tau_old = params.tau
-        P_rep = Psum.repeat(m, 1, 1).contiguous()               # slot = c*q + k  (data movement only)
-        tau_old_rep = tau_old.repeat(m).contiguous()
-        pw = 0.0 if prior_step is None else 1.0 / float(prior_step) ** 2
-        nev = [0]
+            self._tau_ws = (key, _lib.workspace(_lib.lib.pgpfa_tau_solve_workspace_bytes(q, self.T, m)))
+        ts.Psum, ts.tau_old = Psum, params.tau
+        ts.tau, ts.det = empty(q), empty(6, q)
+        ts.flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+        ts.rounds = 0
+        self._tau_rounds(ts, n_blind)
+        return ts
 
-        def fg(cands):                                          # (m,q) -> f, g (m,q)
-            nev[0] += 1
-            c, g = kn.tau_eval(_lib.dev_f64(np.ascontiguousarray(cands).reshape(-1)), P_rep, R, T, EPS_NOISE, pw,
-                               tau_old_rep, self.binSize, ws=self._tau_ws[1])
-            both = torch.stack([c, g]).cpu().numpy()
-            return both[0].reshape(m, q), both[1].reshape(m, q)
+    def mstep_tau(self, params, Psum, numTrials=None, prior_step=None, xtol=1e-10, max_rounds=14, ncand=9):
+        """Returns (tau_seconds (q) as a device tensor, details dict) — see mstep_tau_async."""
+        ts = self.mstep_tau_async(params, Psum, numTrials=numTrials, prior_step=prior_step, xtol=xtol, ncand=ncand)
+        tau = ts.finish(max_rounds=max_rounds)
+        return tau, ts.details()
 
-        oldTau_bins = tau_old.cpu().numpy() * 1000.0 / self.binSize
-        p0 = np.log(1.0 / oldTau_bins ** 2)
-        offs = np.array([0.0, -0.1, 0.1, -0.25, 0.25, -0.5, 0.5, -1.0, 1.0])[:m]
-        cands = p0[None, :] + offs[:, None]
-        f, g = fg(cands)
-        pts = [sorted(zip(cands[:, k], g[:, k], f[:, k])) for k in range(q)]       # per latent: (p, g, f) ascending in p
-        g0, f0 = g[0].copy(), f[0].copy()
-        done = np.zeros(q, dtype=bool)
-        p_star = p0.copy()
-        bracketed = np.zeros(q, dtype=bool)
-
-        def bracket_of(k):
-            """Index i with a sign change of g between pts[k][i] and pts[k][i+1], nearest to p0 on the descent side."""
-            P = pts[k]
-            idx0 = min(range(len(P)), key=lambda i: abs(P[i][0] - p0[k]))
-            if P[idx0][1] == 0.0:
-                return ('exact', idx0)
-            rng = range(idx0, len(P) - 1) if P[idx0][1] < 0 else range(idx0 - 1, -1, -1)
-            for i in rng:
-                if P[i][1] == 0.0:
-                    return ('exact', i)
-                if P[i][1] < 0.0 <= P[i + 1][1]:
-                    return ('br', i)
-            return ('none', len(P) - 1 if P[idx0][1] < 0 else 0)
-
-        def interpolate(k, i):
-            """Zero of g inside (P[i], P[i+1]) by inverse polynomial interpolation through up to 4 neighbours."""
-            P = pts[k]
-            a, ga = P[i][0], P[i][1]
-            b, gb = P[i + 1][0], P[i + 1][1]
-            sel = P[max(0, i - 1):i + 3]
-            gs = np.array([t[1] for t in sel]); ps = np.array([t[0] for t in sel])
-            c = a - ga * (b - a) / (gb - ga)
-            err = 0.5 * (b - a) ** 2                              # secant: error ~ |g''/2g'| (c-a)(b-c)
-            if len(sel) >= 3 and np.all(np.diff(gs) > 0):
-                est = 0.0
-                for u in range(len(sel)):                       # Lagrange form of p(g) at g = 0
-                    wgt = 1.0
-                    for v in range(len(sel)):
-                        if v != u:
-                            wgt *= (0.0 - gs[v]) / (gs[u] - gs[v])
-                    est += wgt * ps[u]
-                if a < est < b:
-                    c = est
-                    span = ps.max() - ps.min()
-                    err = 0.25 * (b - a) ** 2 * span ** (len(sel) - 2)   # ~ product of the distances to the nodes
-            return c, a, b, err
-
-        for rnd in range(max_rounds):
-            cands = np.tile(p_star[None, :], (m, 1))
-            for k in range(q):
-                if done[k]:
-                    continue
-                kind, i = bracket_of(k)
-                P = pts[k]
-                if kind == 'exact':
-                    p_star[k], done[k], bracketed[k] = P[i][0], True, True
-                    continue
-                if kind == 'none':                               # walk further downhill with growing steps
-                    edge = P[i][0]
-                    span = max(0.5, abs(edge - p0[k]))
-                    sgn = 1.0 if P[i][1] < 0 else -1.0
-                    cands[:, k] = np.clip(edge + sgn * span * (0.5 * 1.7 ** np.arange(m)), -40.0, 20.0)
-                    if abs(edge) >= 20.0:
-                        done[k] = True                           # monotone cost: keep the old tau (flagged)
-                    continue
-                bracketed[k] = True
-                c, a, b, err = interpolate(k, i)
-                w = b - a
-                p_star[k] = c
-                if err <= xtol * (1.0 + abs(c)) or w <= xtol * (1.0 + abs(a)):
-                    done[k] = True
-                    continue
-                h1 = min(max(2.0 * err, 4.0 * xtol * (1.0 + abs(c))), w / 16.0)
-                h2 = min(max(4.0 * h1, 0.25 * w ** 2), w / 4.0)
-                hs = [h1, h2] + [min(h2 * 4.0 ** e, w / 2.5) for e in range(1, (m - 1) // 2 - 1)]
-                pr = np.array([c] + [c + sg * hh for hh in hs for sg in (-1.0, 1.0)])[:m]
-                lo, hi = a + 1e-3 * w, b - 1e-3 * w
-                cands[:, k] = np.clip(pr, lo, hi)
-            if done.all():
-                break
-            f, g = fg(cands)
-            for k in range(q):
-                if not done[k]:
-                    have = {t[0] for t in pts[k]}
-                    pts[k] = sorted(pts[k] + [(cands[c_, k], g[c_, k], f[c_, k]) for c_ in range(m) if cands[c_, k] not in have])
-        p_new = np.where(bracketed, p_star, p0)
-        tau_bins = (1.0 / np.exp(p_new)) ** 0.5
-        fun = np.array([min(pts[k], key=lambda t: abs(t[0] - p_new[k]))[2] for k in range(q)])
-        gr = np.array([min(pts[k], key=lambda t: abs(t[0] - p_new[k]))[1] for k in range(q)])
-        details = {'p': p_new, 'p0': p0, 'grad': gr, 'fun': fun, 'fun0': f0, 'grad0': g0, 'nfev': nev[0],
-                   'bracketed': bracketed}
-        return tau_bins * self.binSize / 1000.0, details
+    # ------------------------------------------------------------------ one device-resident EM iteration
+    def em_step(self, params, x0=None, tol=1e-8, cd_tol=1e-10, tau_xtol=1e-10):
+        """One full batch EM iteration (funs/engine.py:180-239: Laplace E-step, C,d M-step, timescale M-step) with the
+        iteration loops driven from the device.  Host synchronisations: one wait inside the E-step driver (the number of
+        trials that need the exact-Newton fallback decides what is enqueued next) and ONE packed read at the end
+        (M-step flags, objective, error codes, and — for the next iteration's prior, already enqueued — positive
+        definiteness and the low-rank ranks).  Returns (new DeviceParams, EStepResult, post_lik, info dict)."""
+        est = self.estep_laplace(params, x0=x0, tol=tol)
+        cd = self.mstep_cd_async(params, est, tol=cd_tol)
+        Psum = self.pautosum(est)
+        ts = self.mstep_tau_async(params, Psum, xtol=tau_xtol)
+        cd.join()
+        q = params.q
+        newp = DeviceParams(cd.th_cur[:, :q].contiguous(), cd.th_cur[:, q].contiguous(), ts.tau, self.T, self.binSize)
+        pend_cd, pend_ts, pend_p = cd.pending(), ts.pending(), newp.pending()
+        cd.join()
+        vals = read_packed(pend_cd + pend_ts + pend_p)
+        v_cd, v_ts, v_p = vals[:len(pend_cd)], vals[len(pend_cd):len(pend_cd) + len(pend_ts)], vals[len(pend_cd) + len(pend_ts):]
+        EStepResult.raise_on(v_cd[2])
+        est._checked = True
+        redo = v_cd[0][0] > 0 or v_ts[0][0] > 0
+        C, d, cost, cd_it, _ = cd.finish(v_cd)
+        tau = ts.finish(v_ts)
+        if redo:                      # a blind schedule was too short (rare): the prior was built from unfinished values
+            newp = DeviceParams(C, d, tau, self.T, self.binSize)
+        else:
+            newp.resolve(v_p)
+        lik = -float(v_cd[2][0]) / self.R_total
+        return newp, est, lik, {"cd_iters": cd_it, "tau_evals": int(ts.flags_host[1]), "cd_cost": cost, "tau_solve": ts}

@@ -1,6 +1,7 @@
 // Handle lifecycle and error reporting of libpgpfa_b200.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "pgpfa_internal.h"
 
@@ -45,6 +46,56 @@ void pgpfa_prof_resolve(pgpfa_handle_t h) {   // call after a stream synchronise
     }
     h->spans.clear();
 }
+
+// ---- progress ring: device -> host counters without stream synchronisation -----------------------
+int pgpfa_prog_alloc(pgpfa_handle_s *h, unsigned long long *seq, int **dev_word) {
+    if (!h || !h->prog_h) return PGPFA_ERR_ARG;
+    const unsigned long long s = h->prog_seq++;
+    h->prog_h[s % PGPFA_PROG_RING] = -1;
+    *seq = s;
+    *dev_word = h->prog_d + (s % PGPFA_PROG_RING);
+    return PGPFA_OK;
+}
+bool pgpfa_prog_peek(pgpfa_handle_s *h, unsigned long long seq, int *value) {
+    const int v = h->prog_h[seq % PGPFA_PROG_RING];
+    if (v < 0) return false;
+    *value = v;
+    return true;
+}
+int pgpfa_prog_wait(pgpfa_handle_s *h, unsigned long long seq, cudaStream_t st, int *value, bool newest) {
+    // `newest`: nothing was enqueued behind the producer of this word, i.e. the wait empties the stream like a
+    // cudaStreamSynchronize (counted as a host synchronisation).  Otherwise it is a throttle: the host is merely too
+    // far ahead, the device still has later iterations queued while the host waits.
+    if (newest) h->n_drain++;
+    if (pgpfa_prog_peek(h, seq, value)) return PGPFA_OK;
+    if (!newest) h->n_throttle++;
+    unsigned long long spins = 0;
+    for (;;) {
+        if (pgpfa_prog_peek(h, seq, value)) return PGPFA_OK;
+        if ((++spins & 0xfff) == 0) {
+            // a faulted or finished stream would never write the word: check instead of spinning forever
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) {
+                if (pgpfa_prog_peek(h, seq, value)) return PGPFA_OK;
+                pgpfa_set_last_cuda_error(cudaErrorUnknown, __FILE__, __LINE__);
+                return PGPFA_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) { pgpfa_set_last_cuda_error(e, __FILE__, __LINE__); return PGPFA_ERR_CUDA; }
+        }
+    }
+}
+int pgpfa_sync(pgpfa_handle_s *h, cudaStream_t st) {
+    if (h) h->n_sync++;
+    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+    return PGPFA_OK;
+}
+extern "C" int pgpfa_set_loop_depth(pgpfa_handle_t h, int depth) {
+    if (!h || depth < 0 || depth > 16) return PGPFA_ERR_ARG;
+    h->loop_depth = depth;
+    return PGPFA_OK;
+}
+extern "C" long long pgpfa_host_sync_count(pgpfa_handle_t h) { return h ? h->n_sync + h->n_drain : -1; }
+extern "C" long long pgpfa_throttle_wait_count(pgpfa_handle_t h) { return h ? h->n_throttle : -1; }
 
 extern "C" int pgpfa_stream_wait_means(pgpfa_handle_t h, cudaStream_t waiting_stream) {
     if (!h) return PGPFA_ERR_ARG;
@@ -103,9 +154,21 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
         delete h;
         return PGPFA_ERR_CUDA;
     }
+    h->prog_h = nullptr; h->prog_d = nullptr; h->prog_seq = 0; h->stage_h = nullptr; h->n_sync = 0; h->n_drain = 0; h->n_throttle = 0;
+    h->loop_depth = 4;
+    if (const char *e = getenv("PGPFA_LOOP_DEPTH")) { const int v = atoi(e); if (v >= 0 && v <= 16) h->loop_depth = v; }
+    {
+        int *ph = nullptr;
+        PGPFA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ph), PGPFA_PROG_RING * sizeof(int), cudaHostAllocMapped));
+        for (int i = 0; i < PGPFA_PROG_RING; i++) ph[i] = -1;
+        h->prog_h = ph;
+        PGPFA_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->prog_d), ph, 0));
+        PGPFA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h->stage_h), PGPFA_STAGE_BYTES, cudaHostAllocDefault));
+    }
     for (int p = 0; p < PGPFA_MAX_PARTS; p++) h->s_part[p] = nullptr;
     PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_means, cudaEventDisableTiming));
+    PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming));
     for (int p = 0; p < PGPFA_MAX_PARTS; p++) {
         PGPFA_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming));
         PGPFA_CUDA_TRY(cudaStreamCreateWithFlags(&h->s_part[p], cudaStreamNonBlocking));
@@ -117,9 +180,12 @@ extern "C" int pgpfa_create(pgpfa_handle_t *out) {
 extern "C" int pgpfa_destroy(pgpfa_handle_t h) {
     if (!h) return PGPFA_OK;
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->prog_h) cudaFreeHost(const_cast<int *>(h->prog_h));
+    if (h->stage_h) cudaFreeHost(h->stage_h);
     if (h->s_part[0]) {
         cudaEventDestroy(h->ev_fork);
         cudaEventDestroy(h->ev_means);
+        cudaEventDestroy(h->ev_stage);
         for (int p = 0; p < PGPFA_MAX_PARTS; p++) {
             if (h->s_part[p]) cudaStreamDestroy(h->s_part[p]);
             cudaEventDestroy(h->ev_join[p]);

@@ -296,11 +296,8 @@ extern "C" int pgpfa_dualvi_eval(pgpfa_handle_t h, const double *lam, const doub
     PGPFA_TRY(vi_carve(workspace, ws_bytes, R, q, T, w, chunk));
     const int n = q * T;
     if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
-    std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, true);
-    if (cov_dense) {
-        PGPFA_CUDA_TRY(cudaMemcpyAsync(w.pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-        PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
-    }
+    const int npairs = pgpfa_i_num_pairs(q, T, true);
+    if (cov_dense) PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, true, st));
     if ((grad || cov_dense) && !vsm) return PGPFA_ERR_ARG;   // the gradient needs the time-diagonal blocks
     VI_DISPATCH(vi_rates_kernel, R, smem_cd(N, q), nullptr, nullptr, lam, y, C, d, nullptr, N, T, 1, nullptr, w.v, w.W, w.sums)
     PGPFA_TRY(pgpfa_i_prior_apply(K, w.v, w.Kv, nullptr, R, q, T, st));
@@ -317,7 +314,7 @@ extern "C" int pgpfa_dualvi_eval(pgpfa_handle_t h, const double *lam, const doub
             PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
             if (cov_dense)
-                PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, nullptr,
+                PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, nullptr,
                                         cov_dense + (size_t)c0 * n * n, n, q, T, cn, st));
         }
     }
@@ -345,9 +342,8 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
     const int n = q * T;
     PGPFA_CUDA_TRY(cudaMemsetAsync(niter, 0, (size_t)R * 4, st));
     PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)R * 4, st));
-    std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, cov_dense != nullptr);
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(w.pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+    const int npairs = pgpfa_i_num_pairs(q, T, cov_dense != nullptr);
+    PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, cov_dense != nullptr, st));
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0 + 1e-6;
     int sweeps = 0, not_converged = 0, total_factor = 0;
@@ -370,7 +366,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
             VI_DISPATCH(vi_s_update_kernel, n_act, (size_t)N * q * sizeof(double), vsm, C, s, act, N, T, tol, w.conv, w.dsmax)
             PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 1, act_next, w.cnt, st));
             PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-            PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+            PGPFA_TRY(pgpfa_sync(h, st));
             n_act = h->pinned[0];
             int *tmp = act; act = act_next; act_next = tmp;
             if (it + 1 > sweeps) sweeps = it + 1;
@@ -388,7 +384,7 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
         PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
         PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
         if (vsmGP || cov_dense)
-            PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,
+            PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, vsmGP,
                                     cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
         // post_lik term: the (offset-free) Laplace objective at the variational mean (funs/inference.py:333)
         PGPFA_TRY(pgpfa_i_prior_apply(Kinv, mean, w.Kx, w.actA, cn, q, T, st));

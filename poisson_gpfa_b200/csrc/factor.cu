@@ -708,9 +708,9 @@ int pgpfa_i_factor(const PgpfaMatSrc &ms, double *L, double *Dinv, double *ZT, c
         // trial-indexed through act; without one trial == slot, so they are shifted as well.
         PgpfaMatSrc m = ms;
         int *inf = info;
+        if (m.dense) m.dense += (size_t)s0 * ms.n * ms.n;      // a dense source is always slot-indexed
         if (!act) {
             if (m.W) m.W += (size_t)s0 * ms.q * ms.q * ms.T;
-            if (m.dense) m.dense += (size_t)s0 * ms.n * ms.n;
             if (inf) inf += s0;
         }
         const int r = factor_one(m, L + s0 * lt, Dinv + s0 * dt, ZT ? ZT + s0 * lt : nullptr, act ? act + s0 : nullptr, inf,

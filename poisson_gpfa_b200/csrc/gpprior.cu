@@ -155,26 +155,20 @@ static int carve_inv_ws(void *workspace, long long ws_bytes, int batch, int n, I
     return PGPFA_OK;
 }
 
-static int upload_pairs(int2 *dst, const std::vector<int2> &pairs, cudaStream_t st) {
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(dst, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
-    return PGPFA_OK;
-}
-
 extern "C" int pgpfa_spd_inverse_batched(const double *A, int batch, int n, double *Ainv, double *logdet, int *info,
                                          void *workspace, long long ws_bytes, cudaStream_t st) {
     if (!A || !Ainv || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
     InvWs w;
     PGPFA_TRY(carve_inv_ws(workspace, ws_bytes, batch, n, w));
-    std::vector<int2> pairs = pgpfa_i_cov_pairs(1, n, true);
-    PGPFA_TRY(upload_pairs(w.pairs, pairs, st));
+    const int npairs = pgpfa_i_num_pairs(1, n, true);
+    PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, 1, n, true, st));        // generated on the device: no host temporary, no sync
     if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)batch * 4, st));
     PgpfaMatSrc ms;
     ms.Kinv = nullptr; ms.W = nullptr; ms.dense = A; ms.q = 1; ms.T = n; ms.n = n; ms.diag_scale = 1.0;
     PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, nullptr, info, batch, st));
     if (logdet) PGPFA_TRY(pgpfa_i_logdet(w.L, n, batch, logdet, st));
     PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, batch, st));
-    PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), nullptr, nullptr, Ainv, n, 1, n, batch, st));
+    PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, nullptr, nullptr, Ainv, n, 1, n, batch, st));
     return PGPFA_OK;
 }
 
@@ -210,11 +204,11 @@ extern "C" int pgpfa_trtri(const double *L, const double *Dinv, double *ZT, int 
 extern "C" int pgpfa_potri_dense(const double *ZT, int batch, int n, double *Ainv, void *workspace, long long ws_bytes,
                                  cudaStream_t st) {
     if (!ZT || !Ainv || !workspace || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
-    std::vector<int2> pairs = pgpfa_i_cov_pairs(1, n, true);
-    if ((size_t)ws_bytes < pairs.size() * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
+    const int npairs = pgpfa_i_num_pairs(1, n, true);
+    if ((size_t)ws_bytes < (size_t)npairs * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
     int2 *dp = reinterpret_cast<int2 *>(align_up(reinterpret_cast<size_t>(workspace)));
-    PGPFA_TRY(upload_pairs(dp, pairs, st));
-    return pgpfa_i_lauum(ZT, dp, (int)pairs.size(), nullptr, nullptr, Ainv, n, 1, n, batch, st);
+    PGPFA_TRY(pgpfa_i_gen_pairs(dp, 1, n, true, st));
+    return pgpfa_i_lauum(ZT, dp, npairs, nullptr, nullptr, Ainv, n, 1, n, batch, st);
 }
 
 extern "C" int pgpfa_cov_slices(const double *ZT, int batch, int q, int T, double *vsm, double *vsmGP, void *workspace,
@@ -223,11 +217,11 @@ extern "C" int pgpfa_cov_slices(const double *ZT, int batch, int q, int T, doubl
     const int n = q * T;
     if (vsm) PGPFA_TRY(pgpfa_i_timediag(ZT, nullptr, vsm, n, q, T, batch, st));
     if (vsmGP) {
-        std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, false);
-        if (!workspace || (size_t)ws_bytes < pairs.size() * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
+        const int npairs = pgpfa_i_num_pairs(q, T, false);
+        if (!workspace || (size_t)ws_bytes < (size_t)npairs * sizeof(int2) + 256) return PGPFA_ERR_WORKSPACE;
         int2 *dp = reinterpret_cast<int2 *>(align_up(reinterpret_cast<size_t>(workspace)));
-        PGPFA_TRY(upload_pairs(dp, pairs, st));
-        PGPFA_TRY(pgpfa_i_lauum(ZT, dp, (int)pairs.size(), nullptr, vsmGP, nullptr, n, q, T, batch, st));
+        PGPFA_TRY(pgpfa_i_gen_pairs(dp, q, T, false, st));
+        PGPFA_TRY(pgpfa_i_lauum(ZT, dp, npairs, nullptr, vsmGP, nullptr, n, q, T, batch, st));
     }
     return PGPFA_OK;
 }

@@ -27,13 +27,17 @@ namespace {
 #define PA_TN 32
 __global__ void __launch_bounds__(128) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
                                                           double *__restrict__ out, const int *act, int nslots, int q,
-                                                          int T) {
+                                                          int T, const int *__restrict__ cnt) {
     __shared__ double As[2][PA_TS][20];
     __shared__ double Bs[2][16][36];
     __shared__ int trial[PA_TN];
     const int k = blockIdx.x, s0 = blockIdx.y * PA_TS, n0 = blockIdx.z * PA_TN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const int fr = lane >> 2, fk = lane & 3;
+    if (cnt) {                                   // device-resident slot count (grid sized by a host upper bound)
+        nslots = min(nslots, *cnt);
+        if (n0 >= nslots) return;
+    }
     if (tid < PA_TN) {
         const int slot = n0 + tid;
         trial[tid] = slot < nslots ? (act ? act[slot] : slot) : -1;
@@ -102,11 +106,13 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
                                                            const double *__restrict__ d, const double *__restrict__ off,
                                                            const int *act, int N, int T,
                                                            double *__restrict__ f, double *__restrict__ g,
-                                                           double *__restrict__ W, LooMap loo) {
+                                                           double *__restrict__ W, LooMap loo,
+                                                           const int *__restrict__ cnt) {
     extern __shared__ double sm[];
     double *Cs = sm;             // N*Q
     double *ds = sm + N * Q;     // N
     __shared__ double red[32];
+    if (cnt && (int)blockIdx.x >= *cnt) return;
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     for (int i = threadIdx.x; i < N * Q; i += blockDim.x) Cs[i] = C[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) ds[i] = d[i];
@@ -168,11 +174,12 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     const double *__restrict__ g, const double *__restrict__ y, const double *__restrict__ C,
     const double *__restrict__ d, const double *__restrict__ off, const int *act, int N, int T, double tol,
     double *__restrict__ fcur, int *__restrict__ conv, int *__restrict__ niter, double *__restrict__ steplen,
-    int step_kind, LooMap loo, double *__restrict__ pcg_s) {
+    int step_kind, LooMap loo, double *__restrict__ pcg_s, const int *__restrict__ cnt) {
     extern __shared__ double sm[];
     double *Cs = sm;
     double *ds = sm + N * Q;
     __shared__ double red[32];
+    if (cnt && (int)blockIdx.x >= *cnt) return;
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     for (int i = threadIdx.x; i < N * Q; i += blockDim.x) Cs[i] = C[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) ds[i] = d[i];
@@ -266,13 +273,19 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
     }
 }
 
-// ordered compaction of the not-yet-converged trials (single CTA)
+// ordered compaction of the not-yet-converged trials (single CTA).  The input length is min(n_in, *n_in_dev) when a
+// device-resident count is given (the host only knows an upper bound); the output count goes to *n_out and, when
+// `prog` is given, to that word of mapped pinned host memory as well, where the host reads it WITHOUT synchronising
+// the stream (it only throttles how far ahead of the device it enqueues, see laplace_solve_impl).
 __global__ void __launch_bounds__(1024) compact_active_kernel(const int *__restrict__ act_in, int n_in,
+                                                              const int *__restrict__ n_in_dev,
                                                               const int *__restrict__ conv, int keep_mask,
-                                                              int *__restrict__ act_out, int *__restrict__ n_out) {
+                                                              int *__restrict__ act_out, int *__restrict__ n_out,
+                                                              volatile int *prog) {
     __shared__ int wsum[32];
     __shared__ int running;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n_in_dev) n_in = min(n_in, *n_in_dev);
     if (tid == 0) running = 0;
     __syncthreads();
     for (int b = 0; b < n_in; b += 1024) {
@@ -290,7 +303,10 @@ __global__ void __launch_bounds__(1024) compact_active_kernel(const int *__restr
         if (tid == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += wsum[w]; running += tot; }
         __syncthreads();
     }
-    if (tid == 0) *n_out = running;
+    if (tid == 0) {
+        *n_out = running;
+        if (prog) { *prog = running; __threadfence_system(); }
+    }
 }
 
 // x <- x + dx for trials whose correction is small (it always is after convergence); records the step
@@ -347,6 +363,23 @@ __global__ void scatter_slots_kernel(const int *act, int n, int *map) {
     if (i < n) map[act[i]] = i;
 }
 
+__global__ void set_count_kernel(int *p, int v) { *p = v; }
+
+// device-side generation of the tile-pair table of pgpfa_i_cov_pairs (same lexicographic order)
+__global__ void gen_pairs_kernel(int2 *pairs, int q, int T, int all, int nb) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int idx = 0;
+    for (int a = 0; a < nb; a++)
+        for (int b = 0; b <= a; b++) {
+            bool in = all != 0;
+            for (int k = 0; k < q && !in; k++) {
+                const int lo = (k * T) >> 6, hi = (k * T + T - 1) >> 6;
+                in = (b >= lo && a <= hi);
+            }
+            if (in) pairs[idx++] = make_int2(a, b);
+        }
+}
+
 __global__ void iota_kernel(int *p, int n, int start) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = start + i;
@@ -391,8 +424,10 @@ __global__ void __launch_bounds__(256) pautosum_kernel(const double *__restrict_
 template <int Q>
 __global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict__ g, double *__restrict__ r,
                                                        double *__restrict__ delta, const int *act, int T, int first_outer,
-                                                       double *__restrict__ pcg_s, int *__restrict__ conv) {
+                                                       double *__restrict__ pcg_s, int *__restrict__ conv,
+                                                       const int *__restrict__ cnt) {
     __shared__ double red[32];
+    if (cnt && (int)blockIdx.x >= *cnt) return;
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     const size_t base = (size_t)trial * Q * T;
     double bb = 0.0;
@@ -415,8 +450,9 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict_
 template <int Q>
 __global__ void __launch_bounds__(256) pcg_dir_kernel(const double *__restrict__ r, const double *__restrict__ z,
                                                       double *__restrict__ p, const int *act, int T, int first,
-                                                      double *__restrict__ pcg_s) {
+                                                      double *__restrict__ pcg_s, const int *__restrict__ cnt) {
     __shared__ double red[32];
+    if (cnt && (int)blockIdx.x >= *cnt) return;
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     const size_t base = (size_t)trial * Q * T;
     double rz = 0.0;
@@ -434,8 +470,9 @@ __global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict_
                                                        const double *__restrict__ W, double *__restrict__ Hp,
                                                        double *__restrict__ delta, double *__restrict__ r,
                                                        const int *act, int T, double *__restrict__ pcg_s,
-                                                       int *__restrict__ conv) {
+                                                       int *__restrict__ conv, const int *__restrict__ cnt) {
     __shared__ double red[32];
+    if (cnt && (int)blockIdx.x >= *cnt) return;
     const int trial = act ? act[blockIdx.x] : blockIdx.x;
     const size_t base = (size_t)trial * Q * T;
     const double *Wt = W + (size_t)trial * Q * Q * T;
@@ -475,22 +512,22 @@ __global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict_
 
 template <int Q>
 int launch_pcg_init(const double *g, double *r, double *delta, const int *act, int nslots, int T, int first_outer,
-                    double *pcg_s, int *conv, cudaStream_t st) {
-    pcg_init_kernel<Q><<<nslots, 256, 0, st>>>(g, r, delta, act, T, first_outer, pcg_s, conv);
+                    double *pcg_s, int *conv, cudaStream_t st, const int *cnt) {
+    pcg_init_kernel<Q><<<nslots, 256, 0, st>>>(g, r, delta, act, T, first_outer, pcg_s, conv, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
 template <int Q>
 int launch_pcg_dir(const double *r, const double *z, double *p, const int *act, int nslots, int T, int first, double *pcg_s,
-                   cudaStream_t st) {
-    pcg_dir_kernel<Q><<<nslots, 256, 0, st>>>(r, z, p, act, T, first, pcg_s);
+                   cudaStream_t st, const int *cnt) {
+    pcg_dir_kernel<Q><<<nslots, 256, 0, st>>>(r, z, p, act, T, first, pcg_s, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
 template <int Q>
 int launch_pcg_step(const double *p, const double *Kp, const double *W, double *Hp, double *delta, double *r, const int *act,
-                    int nslots, int T, double *pcg_s, int *conv, cudaStream_t st) {
-    pcg_step_kernel<Q><<<nslots, 256, 0, st>>>(p, Kp, W, Hp, delta, r, act, T, pcg_s, conv);
+                    int nslots, int T, double *pcg_s, int *conv, cudaStream_t st, const int *cnt) {
+    pcg_step_kernel<Q><<<nslots, 256, 0, st>>>(p, Kp, W, Hp, delta, r, act, T, pcg_s, conv, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -513,11 +550,12 @@ int launch_pcg_step(const double *p, const double *Kp, const double *W, double *
 
 template <int Q>
 int launch_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d, const double *off,
-                const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st, LooMap loo) {
+                const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st, LooMap loo,
+                const int *cnt) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W, loo);
+    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W, loo, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -526,11 +564,11 @@ template <int Q>
 int launch_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g, const double *y,
                       const double *C, const double *d, const double *off, const int *act, int nslots, int N, int T, double tol,
                       double *fcur, int *conv, int *niter, double *steplen, int step_kind, cudaStream_t st, LooMap loo,
-                      double *pcg_s) {
+                      double *pcg_s, const int *cnt) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_linesearch_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, step_kind, loo, pcg_s);
+    laplace_linesearch_kernel<Q><<<nslots, 256, smem, st>>>(x, dx, Kx, Kd, g, y, C, d, off, act, N, T, tol, fcur, conv, niter, steplen, step_kind, loo, pcg_s, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -538,20 +576,20 @@ int launch_linesearch(double *x, const double *dx, const double *Kx, const doubl
 }  // namespace
 
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
-                        cudaStream_t st) {
+                        cudaStream_t st, const int *cnt) {
     if (nslots <= 0) return PGPFA_OK;
     dim3 grid(q, (T + PA_TS - 1) / PA_TS, (nslots + PA_TN - 1) / PA_TN);
-    prior_apply_kernel<<<grid, 128, 0, st>>>(Kmat, v, out, act, nslots, q, T);
+    prior_apply_kernel<<<grid, 128, 0, st>>>(Kmat, v, out, act, nslots, q, T, cnt);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
 
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st, const double *off, LooMap loo) {
+                         cudaStream_t st, const double *off, LooMap loo, const int *cnt) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, off, act, nslots, N, T, f, g, W, st, loo);
+#define CASE_Q(QQ) case QQ: return launch_eval<QQ>(x, Kx, y, C, d, off, act, nslots, N, T, f, g, W, st, loo, cnt);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -561,10 +599,10 @@ int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, con
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int step_kind,
-                       cudaStream_t st, const double *off, LooMap loo, double *pcg_s) {
+                       cudaStream_t st, const double *off, LooMap loo, double *pcg_s, const int *cnt) {
     if (nslots <= 0) return PGPFA_OK;
     switch (q) {
-#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, step_kind, st, loo, pcg_s);
+#define CASE_Q(QQ) case QQ: return launch_linesearch<QQ>(x, dx, Kx, Kd, g, y, C, d, off, act, nslots, N, T, tol, fcur, conv, niter, steplen, step_kind, st, loo, pcg_s, cnt);
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
@@ -579,8 +617,9 @@ int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st) {
 }
 
 // act_out <- the entries of act_in whose state (conv[trial]) has its bit set in keep_mask; *n_out = how many
-int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st) {
-    compact_active_kernel<<<1, 1024, 0, st>>>(act_in, n_in, conv, keep_mask, act_out, n_out);
+int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st,
+                    const int *n_in_dev, int *prog) {
+    compact_active_kernel<<<1, 1024, 0, st>>>(act_in, n_in, n_in_dev, conv, keep_mask, act_out, n_out, prog);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -598,6 +637,14 @@ int pgpfa_i_polish(double *x, const double *dx, const int *act, int n, double ma
                    cudaStream_t st) {
     if (nslots <= 0) return PGPFA_OK;
     polish_kernel<<<nslots, 256, 0, st>>>(x, dx, act, n, max_rel, steplen);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+int pgpfa_i_num_pairs(int q, int T, bool all) { return (int)pgpfa_i_cov_pairs(q, T, all).size(); }
+
+int pgpfa_i_gen_pairs(int2 *pairs_dev, int q, int T, bool all, cudaStream_t st) {
+    gen_pairs_kernel<<<1, 32, 0, st>>>(pairs_dev, q, T, all ? 1 : 0, pgpfa_nb(q * T));
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -710,10 +757,9 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     // fits into the factor area of the workspace; otherwise the dense tiled path
     bool use_lr = lr && lr->r > 0 && posterior_pass && !cov_dense &&
                   pgpfa_i_lowrank_bytes_per_slot(q, T, lr->r) <= per;
-    if (use_lr) PGPFA_TRY(pgpfa_i_lowrank_prepare(*lr, q, T, w.lr_tables, st));
-    std::vector<int2> pairs = pgpfa_i_cov_pairs(q, T, cov_dense != nullptr);
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(w.pairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));   // pairs is a host temporary
+    if (use_lr) PGPFA_TRY(pgpfa_i_lowrank_prepare(h, *lr, q, T, w.lr_tables, st));
+    const int npairs = pgpfa_i_num_pairs(q, T, cov_dense != nullptr);
+    PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, cov_dense != nullptr, st));
 
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
@@ -721,8 +767,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     int total_factor_trials = 0, max_it_used = 0, not_converged = 0, inexact_its = 0, fallback_trials = 0, fresh_sweeps = 0, pcg_its = 0;
     const double solve_bytes = 2.0 * (double)(ltl + nb) * PGPFA_TILE * 8;
     auto read_count = [&](int &dst) -> int {
-        PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PGPFA_CUDA_TRY(cudaStreamSynchronize(st));
+        PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PGPFA_TRY(pgpfa_sync(h, st));
         dst = h->pinned[0];
         pgpfa_prof_resolve(h);
         return PGPFA_OK;
@@ -740,62 +786,126 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         // cond(M^-1 H) ~ 6-10, so a Newton solve to 1e-5 takes ~15 CG iterations, each one fused H v product and
         // two batched T x T mat-vecs: no qT x qT factorisation before the one at the mode.
         if (flags & 1) {
-            for (int it = 0; it < 16 && n_act > 0; it++) {
+            // Control flow: every kernel of this phase reads its slot count from device memory (`cnt` arguments) and
+            // is launched on a grid sized by the host's last known upper bound, so nothing here waits for the stream.
+            // The compaction kernels additionally publish their counts through the handle's progress ring (mapped
+            // pinned memory); the host reads a count `depth` iterations late, only to stop enqueueing and to shrink
+            // grids.  Iterations enqueued after convergence find a zero count and exit at once.  depth = 0 reproduces
+            // the host-driven loop (every count is awaited before the next iteration is enqueued): the iterates are
+            // bit-identical for every depth.
+            const int depth = h->loop_depth;
+            int *cnt_act = w.cnt + 0, *cnt_act_next = w.cnt + 1, *cnt_cg = w.cnt + 2, *cnt_cg_next = w.cnt + 3;
+            set_count_kernel<<<1, 1, 0, st>>>(cnt_act, cn);
+            PGPFA_LAUNCH_CHECK();
+            int ub_act = cn;
+            bool newton_done = false;
+            std::vector<unsigned long long> newton_seq;      // progress words of the Newton-level compactions
+            std::vector<int> cg_in_newton;                   // CG iterations enqueued per Newton iteration
+            std::vector<unsigned long long> cg_seq_all;
+            for (int it = 0; it < 16 && !newton_done; it++) {
+                if (it > 0) {
+                    int nprev = -1;
+                    if (depth == 0) PGPFA_TRY(pgpfa_prog_wait(h, newton_seq.back(), st, &nprev, true));
+                    else if (!pgpfa_prog_peek(h, newton_seq.back(), &nprev)) nprev = -1;
+                    if (nprev == 0) break;
+                    if (nprev > 0) ub_act = nprev;
+                }
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
-                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
-                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo));
-                PCG_DISPATCH(launch_pcg_init, w.g, w.pr, w.dx, act, n_act, T, it == 0, w.pcg_s, w.conv, st)
+                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, ub_act, q, T, st, cnt_act));
+                PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, ub_act, q, N, T, w.fcur, w.g, w.W, st, nullptr, loo, cnt_act));
+                PCG_DISPATCH(launch_pcg_init, w.g, w.pr, w.dx, act, ub_act, T, it == 0, w.pcg_s, w.conv, st, cnt_act)
                 pgpfa_prof_end(h, st);
                 if (it == 0) {
                     pgpfa_prof_begin(h, PGPFA_PROF_BLOCKFACTOR, st);
                     dim3 gwd(q, WD_PARTS);
-                    wdiag_mean_kernel<<<gwd, 256, 0, st>>>(w.W, act, n_act, q, T, w.wbar);
+                    wdiag_mean_kernel<<<gwd, 256, 0, st>>>(w.W, act, cn, q, T, w.wbar);
                     PGPFA_LAUNCH_CHECK();
                     dim3 gsh((T * T + 255) / 256, q);
-                    shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, 1.0 / ((double)n_act * T), T, w.Mk);
+                    shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, 1.0 / ((double)cn * T), T, w.Mk);
                     PGPFA_LAUNCH_CHECK();
                     PGPFA_TRY(pgpfa_spd_inverse_batched(w.Mk, q, T, w.Minv, w.plogdet, w.pinfo, w.pws, w.pws_bytes, st));
                     pgpfa_prof_end(h, st);
                 }
                 // PCG over the trials of this Newton iteration; converged trials drop out of `cg`
                 int *cg = act_next, *cg_next = w.actC;
-                PGPFA_CUDA_TRY(cudaMemcpyAsync(cg, act, (size_t)n_act * sizeof(int), cudaMemcpyDeviceToDevice, st));
-                int n_cg = n_act;
-                for (int ci = 0; ci < 60 && n_cg > 0; ci++) {
+                PGPFA_CUDA_TRY(cudaMemcpyAsync(cg, act, (size_t)ub_act * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                PGPFA_CUDA_TRY(cudaMemcpyAsync(cnt_cg, cnt_act, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                int ub_cg = ub_act;
+                std::vector<unsigned long long> cg_seq;
+                for (int ci = 0; ci < 60; ci++) {
+                    if (ci >= depth + (depth == 0 ? 1 : 0)) {
+                        // count left after CG iteration ci - max(depth, 1); its arrival also implies that the previous
+                        // Newton-level count has been written
+                        int c = 0;
+                        PGPFA_TRY(pgpfa_prog_wait(h, cg_seq[ci - (depth == 0 ? 1 : depth)], st, &c, depth == 0));
+                        if (it > 0 && !newton_done) {
+                            int nprev = 0;
+                            PGPFA_TRY(pgpfa_prog_wait(h, newton_seq.back(), st, &nprev, false));
+                            if (nprev == 0) { newton_done = true; break; }
+                            if (nprev < ub_act) ub_act = nprev;
+                        }
+                        if (c == 0) break;
+                        if (c < ub_cg) ub_cg = c;
+                    }
                     pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
-                    PGPFA_TRY(pgpfa_i_prior_apply(w.Minv, w.pr, w.pz, cg, n_cg, q, T, st));
-                    PCG_DISPATCH(launch_pcg_dir, w.pr, w.pz, w.pp, cg, n_cg, T, ci == 0, w.pcg_s, st)
-                    PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.pp, w.Kd, cg, n_cg, q, T, st));
-                    PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, n_cg, T, w.pcg_s, w.conv, st)
+                    PGPFA_TRY(pgpfa_i_prior_apply(w.Minv, w.pr, w.pz, cg, ub_cg, q, T, st, cnt_cg));
+                    PCG_DISPATCH(launch_pcg_dir, w.pr, w.pz, w.pp, cg, ub_cg, T, ci == 0, w.pcg_s, st, cnt_cg)
+                    PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.pp, w.Kd, cg, ub_cg, q, T, st, cnt_cg));
+                    PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, ub_cg, T, w.pcg_s, w.conv, st, cnt_cg)
                     pgpfa_prof_end(h, st);
-                    compact_active_kernel<<<1, 1024, 0, st>>>(cg, n_cg, w.conv, 1, cg_next, w.cnt);
-                    PGPFA_LAUNCH_CHECK();
-                    PGPFA_TRY(read_count(n_cg));
+                    unsigned long long sq;
+                    int *word;
+                    PGPFA_TRY(pgpfa_prog_alloc(h, &sq, &word));
+                    PGPFA_TRY(pgpfa_i_compact(cg, ub_cg, w.conv, 1, cg_next, cnt_cg_next, st, cnt_cg, word));
+                    cg_seq.push_back(sq);
+                    cg_seq_all.push_back(sq);
                     int *t3 = cg; cg = cg_next; cg_next = t3;
-                    pcg_its++;
-                    if (dbg) fprintf(stderr, "[pgpfa] outer %d cg %d: %d trials still iterating\n", it, ci, n_cg);
+                    int *t4 = cnt_cg; cnt_cg = cnt_cg_next; cnt_cg_next = t4;
                 }
+                cg_in_newton.push_back((int)cg_seq.size());
+                if (newton_done) break;
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
-                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
-                PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
-                                             niter, w.steplen, 2000 + it, st, nullptr, loo, w.pcg_s));
+                PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, ub_act, q, T, st, cnt_act));
+                PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, ub_act, q, N, T, tol, w.fcur, w.conv,
+                                             niter, w.steplen, 2000 + it, st, nullptr, loo, w.pcg_s, cnt_act));
                 pgpfa_prof_end(h, st);
                 int *outp = (act == w.actA) ? w.actB : w.actA;
-                compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, outp, w.cnt);
-                PGPFA_LAUNCH_CHECK();
-                PGPFA_TRY(read_count(n_act));
-                if (dbg) fprintf(stderr, "[pgpfa] outer %d done: %d trials continue\n", it, n_act);
+                unsigned long long sq;
+                int *word;
+                PGPFA_TRY(pgpfa_prog_alloc(h, &sq, &word));
+                PGPFA_TRY(pgpfa_i_compact(act, ub_act, w.conv, 1, outp, cnt_act_next, st, cnt_act, word));
+                newton_seq.push_back(sq);
                 act = outp;
                 act_next = (act == w.actA) ? w.actB : w.actA;
-                inexact_its = it + 1;
+                int *t5 = cnt_act; cnt_act = cnt_act_next; cnt_act_next = t5;
             }
-            // trials that struggled (state 2) or ran out of inexact-Newton iterations (state 0) go to exact Newton
+            // trials that struggled (state 2) or ran out of inexact-Newton iterations (state 0) go to exact Newton.
+            // This count is the one value of the phase the host has to wait for (it decides whether phase B runs).
             iota_kernel<<<(cn + 255) / 256, 256, 0, st>>>(act_next, cn, c0);
             PGPFA_LAUNCH_CHECK();
-            compact_active_kernel<<<1, 1024, 0, st>>>(act_next, cn, w.conv, 5, act, w.cnt);
-            PGPFA_LAUNCH_CHECK();
-            PGPFA_TRY(read_count(n_act));
+            unsigned long long sq;
+            int *word;
+            PGPFA_TRY(pgpfa_prog_alloc(h, &sq, &word));
+            PGPFA_TRY(pgpfa_i_compact(act_next, cn, w.conv, 5, act, w.cnt + 4, st, nullptr, word));
+            PGPFA_TRY(pgpfa_prog_wait(h, sq, st, &n_act, true));
+            pgpfa_prof_resolve(h);
             fallback_trials += n_act;
+            // bookkeeping from the (now complete) progress words: Newton iterations / CG iterations that had work
+            {
+                int prev_n = cn;
+                size_t cgpos = 0;
+                for (size_t i2 = 0; i2 < cg_in_newton.size(); i2++) {
+                    if (prev_n > 0) inexact_its = (int)i2 + 1;
+                    int cprev = prev_n;
+                    for (int c2 = 0; c2 < cg_in_newton[i2]; c2++, cgpos++) {
+                        if (cprev > 0) pcg_its++;
+                        int v = 0;
+                        pgpfa_prog_peek(h, cg_seq_all[cgpos], &v);
+                        cprev = v;
+                    }
+                    if (i2 < newton_seq.size()) { int v = 0; pgpfa_prog_peek(h, newton_seq[i2], &v); prev_n = v; }
+                }
+            }
         }
         // ---- phase B: exact Newton with fresh factorisations; every factor is re-used for a few chord sweeps
         // (4 ms each for 1024 trials) before anything is factorised again
@@ -823,8 +933,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             if (it + 1 > max_it_used) max_it_used = it + 1;
             // sweeps with the factor just computed; `act` keeps the list it was computed for
             int *swp = act_next, *swp_next = w.actC;
-            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 1, swp, w.cnt);
-            PGPFA_LAUNCH_CHECK();
+            PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 1, swp, w.cnt + 8, st));
             int n_swp = 0;
             PGPFA_TRY(read_count(n_swp));
             for (int cs = 0; cs < 8 && n_swp > 0; cs++) {
@@ -841,16 +950,14 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, swp, n_swp, q, N, T, tol, w.fcur, w.conv,
                                              niter, w.steplen, 1000 + cs, st, nullptr, loo));
                 pgpfa_prof_end(h, st);
-                compact_active_kernel<<<1, 1024, 0, st>>>(swp, n_swp, w.conv, 1, swp_next, w.cnt);
-                PGPFA_LAUNCH_CHECK();
+                PGPFA_TRY(pgpfa_i_compact(swp, n_swp, w.conv, 1, swp_next, w.cnt + 8, st));
                 PGPFA_TRY(read_count(n_swp));
                 int *t2 = swp; swp = swp_next; swp_next = t2;
                 fresh_sweeps++;
             }
             // whoever is not converged (state 0: sweeps exhausted, state 2: contraction too slow) is re-factorised
             int *outp = (act == w.actA) ? w.actB : w.actA;       // the sweep lists are dead by now
-            compact_active_kernel<<<1, 1024, 0, st>>>(act, n_act, w.conv, 5, outp, w.cnt);
-            PGPFA_LAUNCH_CHECK();
+            PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 5, outp, w.cnt + 8, st));
             PGPFA_TRY(read_count(n_act));
             act = outp;
             act_next = (act == w.actA) ? w.actB : w.actA;
@@ -865,7 +972,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         pgpfa_prof_end(h, st);
         if (posterior_pass && use_lr) {
             PGPFA_TRY(pgpfa_i_lowrank_posterior(h, *lr, w.W, w.g, x, w.dx, w.actA, cn, q, T, tol, w.steplen, vsm, vsmGP,
-                                                w.L, w.lr_tables, st));
+                                                w.L, w.lr_tables, st, info));
             total_factor_trials += cn;
         } else if (posterior_pass) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
@@ -889,7 +996,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
             PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
             if (vsmGP || cov_dense)
-                PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, (int)pairs.size(), w.actA, vsmGP,
+                PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, vsmGP,
                                         cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
             pgpfa_prof_end(h, st);
         }

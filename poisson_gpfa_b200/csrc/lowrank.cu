@@ -17,6 +17,7 @@
 // All GEMM-shaped steps (F^T Dt F, F L_b^-T, Y_k Y_k^T) run through one batched NT kernel on the FP64 tensor pipe
 // (DMMA.8x8x4); the r x r factorisation and triangular inverse are the tile kernels of factor.cu.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
 #include "pgpfa_internal.h"
@@ -552,16 +553,22 @@ LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
     LR_CASE(9, FN, __VA_ARGS__) LR_CASE(10, FN, __VA_ARGS__) LR_CASE(11, FN, __VA_ARGS__) LR_CASE(12, FN, __VA_ARGS__)
 
 // Uploads the problem tables of the posterior pass (once per E-step; they depend only on the ranks).
-int pgpfa_i_lowrank_prepare(const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st) {
+int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st) {
     const LrTables tb = lr_tables(lr, q, T);
     const size_t qq = (size_t)q * (q + 1);
-    if (3 * qq * sizeof(GemmProb) > PGPFA_LOWRANK_TABLE_BYTES) return PGPFA_ERR_WORKSPACE;
-    GemmProb *d = static_cast<GemmProb *>(probs_dev);
-    if (!tb.cap.empty())
-        PGPFA_CUDA_TRY(cudaMemcpyAsync(d, tb.cap.data(), tb.cap.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(d + qq, tb.yh.data(), tb.yh.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(d + 2 * qq, tb.blk.data(), tb.blk.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
-    PGPFA_CUDA_TRY(cudaStreamSynchronize(st));      // the tables are host temporaries
+    if (3 * qq * sizeof(GemmProb) > PGPFA_LOWRANK_TABLE_BYTES || 3 * qq * sizeof(GemmProb) > PGPFA_STAGE_BYTES)
+        return PGPFA_ERR_WORKSPACE;
+    // staged through the handle's pinned buffer: the copy is asynchronous and needs no stream synchronisation (the
+    // buffer is rewritten at the earliest by the next E-step, whose predecessor has long consumed it: every E-step
+    // ends phase A with a wait for a count produced after this copy)
+    PGPFA_CUDA_TRY(cudaEventSynchronize(h->ev_stage));      // previous use of the staging buffer (long complete)
+    GemmProb *hs = reinterpret_cast<GemmProb *>(h->stage_h);
+    memset(hs, 0, 3 * qq * sizeof(GemmProb));
+    std::copy(tb.cap.begin(), tb.cap.end(), hs);
+    std::copy(tb.yh.begin(), tb.yh.end(), hs + qq);
+    std::copy(tb.blk.begin(), tb.blk.end(), hs + 2 * qq);
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(probs_dev, hs, 3 * qq * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
+    PGPFA_CUDA_TRY(cudaEventRecord(h->ev_stage, st));
     return PGPFA_OK;
 }
 
@@ -571,7 +578,7 @@ int pgpfa_i_lowrank_prepare(const PgpfaLowRank &lr, int q, int T, void *probs_de
 // time-diagonal blocks (event `ev_means` is recorded here: x / vsm final), then the T x T blocks of every latent.
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
-                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st) {
+                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st, int *info) {
     if (nslots <= 0) return PGPFA_OK;
     const int r = lr.r, n = q * T, nbr = pgpfa_nb(r);
     const long long ltr = pgpfa_ltiles(nbr);
@@ -605,7 +612,9 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
     PgpfaMatSrc ms;
     ms.Kinv = nullptr; ms.W = nullptr; ms.dense = G; ms.q = 1; ms.T = r; ms.n = r; ms.diag_scale = 1.0;
     pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
-    PGPFA_TRY(pgpfa_i_factor(ms, Lr, Dr, Zr, nullptr, nullptr, nslots, st, h));
+    // info is trial-indexed through `act`; the dense source G is slot-indexed (factor.cu mat_elem), so passing the
+    // active list only routes a non-positive pivot of slot s to info[act[s]]
+    PGPFA_TRY(pgpfa_i_factor(ms, Lr, Dr, Zr, info ? act : nullptr, info, nslots, st, h));
     pgpfa_prof_end(h, st);
     h->prof_work[PGPFA_PROF_FACTOR] += (double)nslots * r * (double)r * r / 3.0;
     pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);

@@ -9,6 +9,7 @@
 //    :681-769) for all latents at once, on the batched SPD inverse.
 #include "common.cuh"
 #include "pgpfa_internal.h"
+#include "tau_search.h"
 
 using namespace pgpfa;
 
@@ -20,8 +21,10 @@ template <int Q>
 __global__ void __launch_bounds__(256) mstep_cd_stats_kernel(const double *__restrict__ y, const double *__restrict__ m,
                                                              const double *__restrict__ vsm,
                                                              const double *__restrict__ theta, int R, int N, int T,
-                                                             double *__restrict__ partial) {
+                                                             double *__restrict__ partial,
+                                                             const int *__restrict__ skip_if_zero) {
     constexpr int P = Q + 1;
+    if (skip_if_zero && *skip_if_zero == 0) return;       // device-driven Newton loop: every neuron has converged
     constexpr int NS = 1 + P + P * (P + 1) / 2;
     extern __shared__ double sm[];
     double *ys = sm;                          // N x (CD_TT+1)
@@ -98,9 +101,11 @@ __global__ void __launch_bounds__(256) mstep_cd_stats_kernel(const double *__res
     }
 }
 
-__global__ void mstep_cd_reduce_kernel(const double *__restrict__ partial, int nblocks, int len, double *__restrict__ out) {
+__global__ void mstep_cd_reduce_kernel(const double *__restrict__ partial, int nblocks, int len, double *__restrict__ out,
+                                       const int *__restrict__ skip_if_zero) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= len) return;
+    if (skip_if_zero && *skip_if_zero == 0) return;
     double s = 0.0;
     for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * len + i];
     out[i] = s;
@@ -113,11 +118,12 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
                                        double *__restrict__ theta_try, double *__restrict__ fcur,
                                        double *__restrict__ step, double *__restrict__ alpha,
                                        double *__restrict__ slope, int *__restrict__ done, int first, double tol, int N,
-                                       int *__restrict__ n_open) {
+                                       int *__restrict__ n_open, int iter_index) {
     constexpr int P = Q + 1;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     if (done[n]) return;
+    if (iter_index > 0) atomicMax(n_open + 1, iter_index);     // last iteration that still had an open neuron
     // prior: 0.5 pw |theta - theta0|^2 ('useDiag'), or 0.5 (theta-theta0)^T M_n (theta-theta0) with a per-neuron
     // (q+1)x(q+1) matrix M_n (packed upper, pmat[b*N+n]) for the accumulated-Hessian rule ('useHessian')
     double tt[P], t0[P], dl0[P], Md[P];
@@ -304,13 +310,13 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const double *__restric
 #define TAU_PARTS 8
 __global__ void __launch_bounds__(256) tau_trace_kernel(const double *__restrict__ Kinv, const double *__restrict__ dK,
                                                         const double *__restrict__ G, const double *__restrict__ P, int T,
-                                                        double *__restrict__ part) {
+                                                        double *__restrict__ part, int qmod) {
     __shared__ double red[32];
     const int k = blockIdx.x;
-    const size_t off = (size_t)k * T * T;
+    const size_t off = (size_t)k * T * T, poff = (size_t)(k % qmod) * T * T;
     double t1 = 0.0, t2 = 0.0, t3 = 0.0;
     for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < T * T; e += blockDim.x * TAU_PARTS) {
-        const double ki = Kinv[off + e], pp = P[off + e];
+        const double ki = Kinv[off + e], pp = P[poff + e];
         t1 += ki * pp;
         t2 += ki * dK[off + e];
         t3 += G[off + e] * pp;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(256) tau_trace_kernel(const double *__restrict
 __global__ void tau_reduce_kernel(const double *__restrict__ p, const double *__restrict__ part,
                                   const double *__restrict__ logdet, int nslots, double R, double pw,
                                   const double *__restrict__ tau_old, double bs, double *__restrict__ cost,
-                                  double *__restrict__ grad) {
+                                  double *__restrict__ grad, int qmod) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     double t1 = 0.0, t2 = 0.0, t3 = 0.0;
@@ -340,7 +346,7 @@ __global__ void tau_reduce_kernel(const double *__restrict__ p, const double *__
     double g = -dE * exp(p[k]);
     if (pw > 0.0) {
         const double tau = bs / 1000.0 * sqrt(1.0 / exp(p[k]));
-        const double dt = tau - tau_old[k];
+        const double dt = tau - tau_old[k % qmod];
         c += 0.5 * dt * dt * pw;
         g += dt * pw;      // as written in funs/learning.py:734,769 (no chain-rule factor)
     }
@@ -354,11 +360,11 @@ inline int cd_threads(int N) { int t = ((N + 31) / 32) * 32; return t > 256 ? 25
 
 template <int Q>
 int launch_cd_stats(const double *y, const double *m, const double *vsm, const double *theta, int R, int N, int T,
-                    double *partial, int nblocks, cudaStream_t st) {
+                    double *partial, int nblocks, cudaStream_t st, const int *skip_if_zero) {
     const size_t smem = ((size_t)N * (CD_TT + 1) + Q * CD_TT + CD_TT * Q * Q) * sizeof(double);
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(mstep_cd_stats_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mstep_cd_stats_kernel<Q><<<nblocks, cd_threads(N), smem, st>>>(y, m, vsm, theta, R, N, T, partial);
+    mstep_cd_stats_kernel<Q><<<nblocks, cd_threads(N), smem, st>>>(y, m, vsm, theta, R, N, T, partial, skip_if_zero);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -372,40 +378,58 @@ extern "C" long long pgpfa_mstep_cd_workspace_bytes(int q, int N) {
     return (long long)align_up((size_t)cd_blocks() * pgpfa_mstep_cd_nstats(q) * N * 8) + 512;
 }
 
-extern "C" int pgpfa_mstep_cd_stats(const double *y, const double *m, const double *vsm, const double *theta, int R,
-                                    int q, int N, int T, double *stats, void *workspace, long long ws_bytes,
-                                    cudaStream_t st) {
-    if (!y || !m || !vsm || !theta || !stats || !workspace || R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0)
+static int cd_stats_impl(const double *y, const double *m, const double *vsm, const double *theta, int R, int q, int N,
+                         int T, double *stats, void *workspace, long long ws_bytes, cudaStream_t st,
+                         const int *skip_if_zero) {
+    if (!y || !m || !vsm || !theta || !stats || !workspace || R < 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0)
         return PGPFA_ERR_ARG;
     if (ws_bytes < pgpfa_mstep_cd_workspace_bytes(q, N)) return PGPFA_ERR_WORKSPACE;
+    const int len = pgpfa_mstep_cd_nstats(q) * N;
+    if (R == 0) {                  // a rank without trials (mini-batch smaller than the world) contributes zeros
+        PGPFA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)len * 8, st));
+        return PGPFA_OK;
+    }
     double *partial = reinterpret_cast<double *>(align_up(reinterpret_cast<size_t>(workspace)));
     const long long items = (long long)R * ((T + CD_TT - 1) / CD_TT);
     int nblocks = cd_blocks();
     if (items < nblocks) nblocks = (int)items;
     int rc = PGPFA_ERR_ARG;
     switch (q) {
-#define CASE_Q(QQ) case QQ: rc = launch_cd_stats<QQ>(y, m, vsm, theta, R, N, T, partial, nblocks, st); break;
+#define CASE_Q(QQ) case QQ: rc = launch_cd_stats<QQ>(y, m, vsm, theta, R, N, T, partial, nblocks, st, skip_if_zero); break;
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
     }
     PGPFA_TRY(rc);
-    const int len = pgpfa_mstep_cd_nstats(q) * N;
-    mstep_cd_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(partial, nblocks, len, stats);
+    mstep_cd_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(partial, nblocks, len, stats, skip_if_zero);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
+}
+
+extern "C" int pgpfa_mstep_cd_stats(const double *y, const double *m, const double *vsm, const double *theta, int R,
+                                    int q, int N, int T, double *stats, void *workspace, long long ws_bytes,
+                                    cudaStream_t st) {
+    return cd_stats_impl(y, m, vsm, theta, R, q, N, T, stats, workspace, ws_bytes, st, nullptr);
+}
+
+/* same, as one iteration of a device-driven Newton loop: when *n_open (device int, written by pgpfa_mstep_cd_update)
+ * is zero the launch exits at once and leaves `stats` untouched */
+extern "C" int pgpfa_mstep_cd_stats_gated(const double *y, const double *m, const double *vsm, const double *theta, int R,
+                                          int q, int N, int T, double *stats, void *workspace, long long ws_bytes,
+                                          const int *n_open, cudaStream_t st) {
+    return cd_stats_impl(y, m, vsm, theta, R, q, N, T, stats, workspace, ws_bytes, st, n_open);
 }
 
 extern "C" int pgpfa_mstep_cd_update(const double *stats, double inv_R, double prior_w, const double *prior_mat,
                                      const double *theta0,
                                      double *theta_cur, double *theta_try, double *fcur, double *step, double *alpha,
                                      double *slope, int *done, int first, double tol, int N, int q, int *n_open,
-                                     cudaStream_t st) {
+                                     int iter_index, cudaStream_t st) {
     if (!stats || !theta0 || !theta_cur || !theta_try || !fcur || !step || !alpha || !slope || !done || !n_open)
         return PGPFA_ERR_ARG;
     PGPFA_CUDA_TRY(cudaMemsetAsync(n_open, 0, sizeof(int), st));
     const int blocks = (N + 63) / 64;
     switch (q) {
-#define CASE_Q(QQ) case QQ: mstep_cd_update_kernel<QQ><<<blocks, 64, 0, st>>>(stats, inv_R, prior_w, prior_mat, theta0, theta_cur, theta_try, fcur, step, alpha, slope, done, first, tol, N, n_open); break;
+#define CASE_Q(QQ) case QQ: mstep_cd_update_kernel<QQ><<<blocks, 64, 0, st>>>(stats, inv_R, prior_w, prior_mat, theta0, theta_cur, theta_try, fcur, step, alpha, slope, done, first, tol, N, n_open, iter_index); break;
         PGPFA_FOR_EACH_Q(CASE_Q)
 #undef CASE_Q
         default: return PGPFA_ERR_ARG;
@@ -421,9 +445,9 @@ extern "C" long long pgpfa_tau_eval_workspace_bytes(int q, int T) {
            pgpfa_spd_inverse_workspace_bytes(q, T) + 1024;
 }
 
-extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTrials, int q, int T, double eps,
-                              double prior_w, const double *tau_old, double bs, double *cost, double *grad,
-                              void *workspace, long long ws_bytes, cudaStream_t st) {
+static int tau_eval_impl(const double *p, const double *Psum, double numTrials, int q, int qmod, int T, double eps,
+                         double prior_w, const double *tau_old, double bs, double *cost, double *grad, void *workspace,
+                         long long ws_bytes, cudaStream_t st) {
     if (!p || !Psum || !cost || !grad || !workspace || q <= 0 || T <= 0) return PGPFA_ERR_ARG;
     if (prior_w > 0.0 && !tau_old) return PGPFA_ERR_ARG;
     if (ws_bytes < pgpfa_tau_eval_workspace_bytes(q, T)) return PGPFA_ERR_WORKSPACE;
@@ -446,9 +470,133 @@ extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTri
     small_gemm_kernel<<<grid, 128, 0, st>>>(M1, Kinv, G, T);
     PGPFA_LAUNCH_CHECK();
     dim3 gtr(q, TAU_PARTS);
-    tau_trace_kernel<<<gtr, 256, 0, st>>>(Kinv, dK, G, Psum, T, part);
+    tau_trace_kernel<<<gtr, 256, 0, st>>>(Kinv, dK, G, Psum, T, part, qmod);
     PGPFA_LAUNCH_CHECK();
-    tau_reduce_kernel<<<(q + 127) / 128, 128, 0, st>>>(p, part, logdet, q, numTrials, prior_w, tau_old, bs, cost, grad);
+    tau_reduce_kernel<<<(q + 127) / 128, 128, 0, st>>>(p, part, logdet, q, numTrials, prior_w, tau_old, bs, cost, grad, qmod);
     PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
+extern "C" int pgpfa_tau_eval(const double *p, const double *Psum, double numTrials, int q, int T, double eps,
+                              double prior_w, const double *tau_old, double bs, double *cost, double *grad,
+                              void *workspace, long long ws_bytes, cudaStream_t st) {
+    return tau_eval_impl(p, Psum, numTrials, q, q, T, eps, prior_w, tau_old, bs, cost, grad, workspace, ws_bytes, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-driven C,d Newton loop and timescale search (no host reads inside; funs/learning.py:124-130, :283-288)
+// ---------------------------------------------------------------------------------------------
+/* n_iters Newton iterations on every neuron, starting with iteration index first_iter (1 = the first one of a
+ * solve: theta_cur = theta_try = theta0, done = 0, n_open[0..3] = 0 set by the caller).  Each iteration is
+ * pgpfa_mstep_cd_stats_gated + pgpfa_mstep_cd_update; once every neuron has converged the remaining iterations are
+ * empty launches.  n_open (device int[4]): [0] neurons still open after the last iteration, [1] index of the last
+ * iteration that had an open neuron.  Single-rank only (with trial sharding the statistics have to be all-reduced
+ * between the two calls: poisson_gpfa_b200/core.py runs the same two entry points around the collective). */
+extern "C" int pgpfa_mstep_cd_solve(const double *y, const double *post_mean, const double *vsm, int R, int q, int N, int T,
+                                    double inv_R, double prior_w, const double *prior_mat, const double *theta0,
+                                    double *theta_cur, double *theta_try, double *fcur, double *step, double *alpha,
+                                    double *slope, int *done, int *n_open, double *stats, int first_iter, int n_iters,
+                                    double tol, void *workspace, long long ws_bytes, cudaStream_t st) {
+    if (first_iter < 1 || n_iters < 0) return PGPFA_ERR_ARG;
+    for (int it = first_iter; it < first_iter + n_iters; it++) {
+        PGPFA_TRY(cd_stats_impl(y, post_mean, vsm, theta_try, R, q, N, T, stats, workspace, ws_bytes, st,
+                                it == 1 ? nullptr : n_open));
+        PGPFA_TRY(pgpfa_mstep_cd_update(stats, inv_R, prior_w, prior_mat, theta0, theta_cur, theta_try, fcur, step, alpha,
+                                        slope, done, it == 1 ? 1 : 0, tol, N, q, n_open, it, st));
+    }
+    return PGPFA_OK;
+}
+
+namespace {
+// one thread per latent; phase 0: first candidates, phase 1: merge the round-0 evaluation and propose, phase >= 2:
+// merge a later round and propose.  cands / cost / grad are (m, q) with slot = c*q + k.
+// flags (device int[4]): [0] latents still open, [1] evaluations that had an open latent (nfev),
+// [2] bit k set: a sign change of the gradient was bracketed for latent k, [3] bit k set: the search walked to the
+// edge of the admissible range without one (the old timescale is kept).
+__global__ void tau_ctrl_kernel(TauLatent *st, int q, int m, int phase, const double *__restrict__ tau_old, double bs,
+                                double xtol, double *__restrict__ cands, const double *__restrict__ cost,
+                                const double *__restrict__ grad, int *__restrict__ flags, double *__restrict__ tau_new,
+                                double *__restrict__ details) {
+    __shared__ int s_open, s_br, s_walk;
+    const int k = threadIdx.x;
+    if (k == 0) { s_open = 0; s_br = 0; s_walk = 0; }
+    __syncthreads();
+    double c[TAU_MAXC];
+    if (k < q) {
+        TauLatent &s = st[k];
+        if (phase == 0) {
+            tau_init(s, tau_old[k], bs, m, c);
+            for (int i = 0; i < m; i++) cands[i * q + k] = c[i];
+            atomicAdd(&s_open, 1);
+        } else {
+            const bool was_open = flags[0] > 0;
+            if (was_open) {
+                double g[TAU_MAXC], f[TAU_MAXC];
+                for (int i = 0; i < m; i++) { c[i] = cands[i * q + k]; g[i] = grad[i * q + k]; f[i] = cost[i * q + k]; }
+                tau_merge(s, m, c, g, f, phase == 1);
+                const int dn = tau_next(s, m, xtol, c);
+                for (int i = 0; i < m; i++) cands[i * q + k] = c[i];
+                if (!dn) atomicAdd(&s_open, 1);
+            }
+            if (s.bracketed) atomicOr(&s_br, 1 << k);
+            if (s.walked_out) atomicOr(&s_walk, 1 << k);
+            double p_new, fun, gr;
+            tau_result(s, p_new, fun, gr);
+            tau_new[k] = sqrt(1.0 / exp(p_new)) * bs / 1000.0;
+            details[0 * q + k] = p_new; details[1 * q + k] = s.p0; details[2 * q + k] = gr; details[3 * q + k] = fun;
+            details[4 * q + k] = s.f0; details[5 * q + k] = s.g0;
+        }
+    }
+    __syncthreads();
+    if (k == 0) {
+        if (phase == 0) { flags[0] = s_open; flags[1] = 1; flags[2] = 0; flags[3] = 0; }
+        else {
+            const bool was_open = flags[0] > 0;
+            flags[0] = was_open ? s_open : 0;
+            if (was_open && s_open > 0) flags[1] += 1;
+            flags[2] = s_br; flags[3] = s_walk;
+        }
+    }
+}
+}  // namespace
+
+extern "C" long long pgpfa_tau_solve_workspace_bytes(int q, int T, int m) {
+    if (q <= 0 || q > PGPFA_QMAX || T <= 0 || m < 5 || m > TAU_MAXC || !(m & 1)) return -1;
+    return pgpfa_tau_eval_workspace_bytes(q * m, T) + (long long)align_up((size_t)q * sizeof(TauLatent)) +
+           3 * (long long)align_up((size_t)q * m * 8) + 1024;
+}
+
+/* GP-timescale M-step for all latents on the device (funs/learning.py:257-293; prior variant :771-830 with
+ * prior_w = 1/step^2): rounds of [m candidate points per latent -> one batched cost/gradient evaluation -> bracket /
+ * inverse-interpolation controller (tau_search.h)].  first_round = 0 starts a search (n_rounds evaluations follow);
+ * a later call with first_round = the number of evaluations done so far continues it on the SAME workspace.
+ * Nothing is read by the host: flags (device int[4]) = {latents still open, evaluations used, bracketed mask,
+ * walked-out mask}; tau_new (q, seconds) and details (6, q) = {p, p0, grad, fun, fun0, grad0} are refreshed after
+ * every round.  Rounds issued after every latent is done re-evaluate the final points and change nothing. */
+extern "C" int pgpfa_mstep_tau_solve(const double *Psum, const double *tau_old, double numTrials, int q, int T, double eps,
+                                     double prior_w, double bs, double xtol, int m, int first_round, int n_rounds,
+                                     double *tau_new, double *details, int *flags, void *workspace, long long ws_bytes,
+                                     cudaStream_t st) {
+    if (!Psum || !tau_old || !tau_new || !details || !flags || !workspace || first_round < 0 || n_rounds < 0)
+        return PGPFA_ERR_ARG;
+    const long long need = pgpfa_tau_solve_workspace_bytes(q, T, m);
+    if (need < 0) return PGPFA_ERR_ARG;
+    if (ws_bytes < need) return PGPFA_ERR_WORKSPACE;
+    unsigned char *w = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(workspace)));
+    TauLatent *state = (TauLatent *)w; w += align_up((size_t)q * sizeof(TauLatent));
+    double *cands = (double *)w; w += align_up((size_t)q * m * 8);
+    double *cost = (double *)w; w += align_up((size_t)q * m * 8);
+    double *grad = (double *)w; w += align_up((size_t)q * m * 8);
+    const long long ev_bytes = pgpfa_tau_eval_workspace_bytes(q * m, T);
+    if (first_round == 0) {
+        tau_ctrl_kernel<<<1, 32, 0, st>>>(state, q, m, 0, tau_old, bs, xtol, cands, cost, grad, flags, tau_new, details);
+        PGPFA_LAUNCH_CHECK();
+    }
+    for (int r = first_round; r < first_round + n_rounds; r++) {
+        PGPFA_TRY(tau_eval_impl(cands, Psum, numTrials, q * m, q, T, eps, prior_w, tau_old, bs, cost, grad, w, ev_bytes, st));
+        tau_ctrl_kernel<<<1, 32, 0, st>>>(state, q, m, r == 0 ? 1 : 2, tau_old, bs, xtol, cands, cost, grad, flags, tau_new,
+                                          details);
+        PGPFA_LAUNCH_CHECK();
+    }
     return PGPFA_OK;
 }

@@ -47,8 +47,22 @@ enum {
 #define PGPFA_MAX_PARTS 4
 struct PgpfaProfSpan { cudaEvent_t e0, e1; int slot; };
 
+#define PGPFA_PROG_RING 4096          // progress words (ints) in mapped pinned memory
+#define PGPFA_STAGE_BYTES 65536        // pinned staging for small host -> device tables (truly asynchronous copies)
 struct pgpfa_handle_s {
     int *pinned;        // small pinned host scratch for device -> host counters
+    // Device -> host progress without stream synchronisation: compaction kernels write the number of still-active
+    // trials into a ring of words in mapped pinned memory (prog_h = host view, prog_d = device view); the host
+    // drivers read them to stop enqueueing / shrink grids and never wait for an empty stream inside a loop.
+    volatile int *prog_h;
+    int *prog_d;
+    unsigned long long prog_seq;
+    cudaEvent_t ev_stage;                   // completion of the last copy out of stage_h
+    unsigned char *stage_h;                 // pinned staging buffer (PGPFA_STAGE_BYTES)
+    int loop_depth;                         // how many loop iterations the drivers enqueue ahead of the last count read
+    long long n_sync;                       // cudaStreamSynchronize / cudaDeviceSynchronize calls made by the library
+    long long n_drain;                      // blocking reads of the NEWEST progress word (the stream runs empty: a sync)
+    long long n_throttle;                   // blocking reads of an older word (device still has queued work: no sync)
     int device;
     bool profiling;
     double prof_ms[PGPFA_PROF_SLOTS];
@@ -59,6 +73,14 @@ struct pgpfa_handle_s {
     cudaEvent_t ev_fork, ev_join[PGPFA_MAX_PARTS];
     cudaEvent_t ev_means;                   // recorded after the time-diagonal kernel of a Laplace solve
 };
+// progress ring (api.cu): allocate a word (reset to -1), blocking / non-blocking read
+int pgpfa_prog_alloc(pgpfa_handle_s *h, unsigned long long *seq, int **dev_word);
+int pgpfa_prog_wait(pgpfa_handle_s *h, unsigned long long seq, cudaStream_t st, int *value, bool newest);
+bool pgpfa_prog_peek(pgpfa_handle_s *h, unsigned long long seq, int *value);
+int pgpfa_sync(pgpfa_handle_s *h, cudaStream_t st);      // counted cudaStreamSynchronize
+// device-generated tile-pair table of pgpfa_i_cov_pairs (same order), no host temporary, no synchronisation
+int pgpfa_i_gen_pairs(int2 *pairs_dev, int q, int T, bool all, cudaStream_t st);
+int pgpfa_i_num_pairs(int q, int T, bool all);
 void pgpfa_prof_begin(pgpfa_handle_t h, int slot, cudaStream_t st);
 void pgpfa_prof_end(pgpfa_handle_t h, cudaStream_t st);
 void pgpfa_prof_resolve(pgpfa_handle_t h);
@@ -67,15 +89,18 @@ void pgpfa_prof_resolve(pgpfa_handle_t h);
 struct LooMap { const int *ymap; const int *excl; };
 static inline LooMap pgpfa_no_loo() { LooMap l; l.ymap = nullptr; l.excl = nullptr; return l; }
 
+// `cnt` (optional, device): the true number of slots; nslots is then only the host's upper bound that sizes the grid
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
-                        cudaStream_t st);
+                        cudaStream_t st, const int *cnt = nullptr);
 int pgpfa_i_laplace_eval(const double *x, const double *Kx, const double *y, const double *C, const double *d,
                          const int *act, int nslots, int q, int N, int T, double *f, double *g, double *W,
-                         cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo());
+                         cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo(),
+                         const int *cnt = nullptr);
 int pgpfa_i_linesearch(double *x, const double *dx, const double *Kx, const double *Kd, const double *g,
                        const double *y, const double *C, const double *d, const int *act, int nslots, int q, int N,
                        int T, double tol, double *fcur, int *conv, int *niter, double *steplen, int step_kind,
-                       cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo(), double *pcg_s = nullptr);
+                       cudaStream_t st, const double *off = nullptr, LooMap loo = pgpfa_no_loo(), double *pcg_s = nullptr,
+                       const int *cnt = nullptr);
 int pgpfa_i_pautosum(const double *vsmGP, const double *m, int R, int q, int T, int accumulate, double *P,
                      cudaStream_t st);
 std::vector<int2> pgpfa_i_cov_pairs(int q, int T, bool all);
@@ -91,9 +116,11 @@ struct PgpfaLowRank {
 };
 #define PGPFA_LOWRANK_TABLE_BYTES 65536
 size_t pgpfa_i_lowrank_bytes_per_slot(int q, int T, int r);
-int pgpfa_i_lowrank_prepare(const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st);
+int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st);
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
-                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st);
+                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st,
+                              int *info = nullptr);
 int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st);
-int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st);
+int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st,
+                    const int *n_in_dev = nullptr, int *prog = nullptr);

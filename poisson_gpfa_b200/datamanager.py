@@ -70,7 +70,7 @@ class StevensonDataset():
                           _lib.dev_f64(np.asarray(t0)), trialDur / 1000, R, ydim, T)
         Yh = Y.cpu().numpy().astype(np.int64)
         self.data = [{'Y': Yh[r], 'spike_time': spike_time[r]} for r in range(R)]
-        self.__dict__['_pgpfa_y'] = Y               # counts are already resident on the device
+        self.__dict__['_pgpfa_y'] = (Y, self.data)  # counts are already resident on the device (cache tied to this list)
         self.trialDur = trialDur
         self.binSize = binSize
         self.numTrials = int(numTrials / 2)

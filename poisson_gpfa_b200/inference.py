@@ -25,17 +25,21 @@ def _host_rows(experiment, lo, hi):
     Y_all = getattr(experiment, 'Y_all', None)
     if Y_all is not None:          # optional fast path: all counts as one (R,N,T) array or pinned tensor
         return torch.as_tensor(Y_all)[lo:hi]
+    if hi <= lo:                   # a rank without trials (fewer trials than ranks)
+        N, T = np.shape(experiment.data[0]['Y']) if len(experiment.data) else (0, 0)
+        return torch.zeros(0, N, T, dtype=torch.float64)
     return torch.from_numpy(np.stack([np.asarray(experiment.data[r]['Y'], dtype=np.float64) for r in range(lo, hi)]))
 
 
 def _full_counts(experiment):
     """All trials of an experiment as one (R,N,T) float64 device tensor, uploaded once and cached on the experiment
     object.  Only needed for parents of mini-batches (util.subsampleTrials), which are gathered on the device."""
-    y = experiment.__dict__.get('_pgpfa_y')
-    if y is None or y.shape[0] != len(experiment.data):
+    cached = experiment.__dict__.get('_pgpfa_y')
+    if cached is None or cached[1] is not experiment.data:
         y = _host_rows(experiment, 0, len(experiment.data)).to(device="cuda", dtype=torch.float64).contiguous()
-        experiment.__dict__['_pgpfa_y'] = y
-    return y
+        cached = (y, experiment.data)
+        experiment.__dict__['_pgpfa_y'] = cached
+    return cached[0]
 
 
 def upload_counts(experiment):
@@ -54,7 +58,10 @@ def device_trials(experiment, reducer=None):
     reducer = reducer if reducer is not None else Reducer()
     R = len(experiment.data)
     cached = experiment.__dict__.get('_pgpfa_dev')
-    if cached is not None and cached.R_total == R and cached.reducer.world_size == reducer.world_size:
+    # the cache is tied to the very list of trials it was built from (a re-assigned experiment.data, even of the same
+    # length, is a different data set)
+    if (cached is not None and cached.R_total == R and cached.reducer.world_size == reducer.world_size
+            and getattr(cached, '_data_ref', None) is experiment.data):
         return cached
     lo, hi = shard_bounds(R, reducer.world_size, reducer.rank)
     parent = experiment.__dict__.get('_pgpfa_parent')
@@ -63,7 +70,10 @@ def device_trials(experiment, reducer=None):
         y = _full_counts(parent).index_select(0, idx).contiguous()
     else:
         y = _host_rows(experiment, lo, hi).to(device="cuda", dtype=torch.float64).contiguous()
+    if parent is not None and hasattr(experiment, 'batchTrIdx') and y.shape[0] == 0:
+        y = y.reshape(0, *_full_counts(parent).shape[1:])
     dt = DeviceTrials(y, experiment.binSize, reducer, R_total=R, offset=lo)
+    dt._data_ref = experiment.data
     experiment.__dict__['_pgpfa_dev'] = dt
     return dt
 
@@ -192,7 +202,9 @@ def laplace(experiment, params, prevOptimRes=None, returnOptimRes=True, verbose=
 
     The per-trial scipy Newton-CG loop is replaced by one batched exact-Newton solve on the device
     (``optimMethod`` is accepted for signature compatibility).  ``tol`` bounds the last Newton step
-    (relative, inf-norm); the returned mode is quadratically closer than that."""
+    (relative, inf-norm); the returned mode is quadratically closer than that, and the covariances (evaluated one
+    step earlier) are within ~tol of the converged ones.  Failures (a Hessian that is not positive definite, the
+    iteration limit, a non-finite objective) raise here, on every rank of a sharded run."""
     trials = device_trials(experiment, reducer)
     T = trials.T
     p = device_params(params, T, experiment.binSize)

@@ -178,13 +178,19 @@ class LaplaceResult:
     __slots__ = ("x", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc")
 
 
-def prior_lowrank(K, eps=0.001, delta=1e-14):
-    """Pivoted Cholesky K_k - eps I = F_k F_k^T (pgpfa_prior_lowrank).  Returns (F, Ft, ranks) with ranks a host list."""
+def prior_lowrank_async(K, eps=0.001, delta=1e-14):
+    """Pivoted Cholesky K_k - eps I = F_k F_k^T (pgpfa_prior_lowrank), enqueued only: (F, Ft, ranks as a DEVICE tensor)."""
     q, T, _ = K.shape
     F, Ft = empty(q, T, T), empty(q, T, T)
     rank = empty(q, dtype=torch.int32)
     call("pgpfa_prior_lowrank", ptr(K), q, T, float(eps), float(delta), ptr(F), ptr(Ft), ptr(rank), stream())
-    return F, Ft, [int(v) for v in rank.cpu().tolist()]
+    return F, Ft, rank
+
+
+def prior_lowrank(K, eps=0.001, delta=1e-14):
+    """Same with the ranks read back: (F, Ft, ranks as a host list)."""
+    F, Ft, rank = prior_lowrank_async(K, eps, delta)
+    return F, Ft, [int(v) for v in _lib.to_host(rank)]
 
 
 def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True, want_vsmGP=True, want_cov=False,

@@ -195,6 +195,7 @@ def _learn_tau(oldParams, infRes, experiment, prior_step=None):
     p = device_params(oldParams, trials.T, experiment.binSize)
     Psum = trials.pautosum(est)
     tau, det = trials.mstep_tau(p, Psum, prior_step=prior_step)
+    tau = _lib.to_host(tau)
     details = [OptimizeDetail(x=np.array([det['p'][k]]), fun=det['fun'][k], jac=np.array([det['grad'][k]]),
                               nfev=det['nfev'], success=bool(det['bracketed'][k])) for k in range(p.q)]
     return tau, details

@@ -53,6 +53,9 @@ def seenTrials(experiment, seenIdx):
     out = copy.copy(experiment)
     out.data = [experiment.data[i] for i in idx]
     out.numTrials = len(out.data)
+    # the copy must not inherit the parent's device caches or its stacked counts (they describe OTHER trials)
+    for key in ('_pgpfa_dev', '_pgpfa_y', 'Y_all'):
+        out.__dict__.pop(key, None)
     return out
 
 

@@ -113,9 +113,10 @@ def test_engine_batch_free_running(name, q, N, T):
     for it in range(n_iter):
         params, lik, x0s, _ = po.em_step_struct(ys, params, T, ex.binSize, x0s)
         assert abs(fit.posteriorLikelihood[it] - lik) <= 1e-9 * abs(lik)
-        assert rel(fit.paramSeq[it + 1]['C'], params['C']) <= 1e-7
-        assert rel(fit.paramSeq[it + 1]['d'], params['d']) <= 1e-7
-        assert rel(fit.paramSeq[it + 1]['tau'], params['tau']) <= 1e-7
+        # free-running: both sides start each iteration from their OWN previous iterate, deviations compound
+        assert rel(fit.paramSeq[it + 1]['C'], params['C']) <= 1e-8
+        assert rel(fit.paramSeq[it + 1]['d'], params['d']) <= 1e-8
+        assert rel(fit.paramSeq[it + 1]['tau'], params['tau']) <= 1e-8
     # the stock reference (default scipy tolerances) lands within its own optimiser slack of the same point
     assert rel(fit.optimParams['C'], g['stock_C']) <= 5e-3
     assert rel(fit.optimParams['tau'], g['stock_tau']) <= 5e-3
@@ -160,11 +161,14 @@ def test_config3_shape_small_trial_count():
     p_o, lik_o, _, ir = po.em_step_struct(ys, copy.deepcopy(params), 200, 10)
     assert rel(np.stack(list(infRes['post_mean'])), np.stack(ir['post_mean'])) <= 1e-8
     assert rel(np.stack(list(infRes['post_vsm'])), np.stack(ir['post_vsm'])) <= 1e-8
+    # the low-rank posterior pass (the path bench.py times) DIRECTLY against the oracle's dense inverse
+    assert infRes.device.stats["lowrank_r"] > 0
+    assert rel(np.stack(list(infRes['post_vsmGP'])), np.stack(ir['post_vsmGP'])) <= 1e-8
     assert abs(lik - lik_o) <= 1e-10 * abs(lik_o)
     assert rel(newParams['C'], p_o['C']) <= 1e-8 and rel(newParams['d'], p_o['d']) <= 1e-8
-    # tau: the stationarity condition is a difference of O(R T) traces through K^-1 (cond ~1e5); its zero is
-    # defined to ~1e-8 relative at best on either side
-    assert rel(newParams['tau'], p_o['tau']) <= 1e-7
+    # tau at the north-star tolerance: the float64 root of the stationarity condition is the exact root to 1e-12
+    # (tests/test_tau_search_host.py); round 1's 1e-7 was the oracle's BFGS stopping early, not the device
+    assert rel(newParams['tau'], p_o['tau']) <= 1e-8
 
 
 @pytest.mark.parametrize("method", ["hess", "grad"])
@@ -272,7 +276,7 @@ def test_side_stream_mstep_is_bit_identical_to_single_stream(monkeypatch):
             tau, _ = trials.mstep_tau(params, trials.pautosum(est))
             params = core.DeviceParams(C, d, tau, ex.T, ex.binSize)
             x0 = est.x
-            out.append((lik, cost, C.cpu().numpy(), d.cpu().numpy(), np.asarray(tau), est.vsmGP.cpu().numpy()))
+            out.append((lik, cost, C.cpu().numpy(), d.cpu().numpy(), tau.cpu().numpy(), est.vsmGP.cpu().numpy()))
         return out
 
     a, b = run("1"), run("0")

@@ -54,7 +54,7 @@ def test_laplace_edge_shapes(q, N, T, R, dOffset):
     assert rel(C, C_o) <= 1e-8 and rel(d, d_o) <= 1e-8
     tau, det = trials.mstep_tau(p, trials.pautosum(est))
     tau_o, _ = po.learn_tau(params, ir, 10, gtol=1e-11)
-    assert rel(tau, tau_o) <= 1e-7
+    assert rel(tau, tau_o) <= 1e-8
 
 
 def test_unsupported_latent_dimension_and_bad_inputs_fail_loudly():

@@ -80,8 +80,8 @@ def test_variational_em_engine():
         C, d, _ = po.learn_Cd_newton(params, ys, infRes['post_mean'], infRes['post_vsm'])
         tau, _ = po.learn_tau(params, infRes, ex.binSize, gtol=1e-11)
         params = {'C': C, 'd': d, 'tau': tau}
-        assert rel(fit.paramSeq[it + 1]['C'], C) <= 1e-7 and rel(fit.paramSeq[it + 1]['d'], d) <= 1e-7
-        assert rel(fit.paramSeq[it + 1]['tau'], tau) <= 1e-7
+        assert rel(fit.paramSeq[it + 1]['C'], C) <= 1e-8 and rel(fit.paramSeq[it + 1]['d'], d) <= 1e-8
+        assert rel(fit.paramSeq[it + 1]['tau'], tau) <= 1e-8
 
 
 def test_variational_config4_shape_small():

@@ -128,7 +128,7 @@ def test_c_abi_exports_every_declared_symbol():
     dll = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(dll, name), name
-    assert dll.pgpfa_abi_version() == 1
+    assert dll.pgpfa_abi_version() == 2
     assert b"no CPU fallback" in _lib.lib.pgpfa_error_string(6)
 
 
