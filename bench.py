@@ -1,16 +1,19 @@
 #!/usr/bin/env python
-"""Headline benchmark: EM iterations / second of full-batch Laplace EM (E-step + M-step) on
-1024 trials, q=8 latents, N=100 neurons, T=200 bins (BASELINE.json configs[2]), synthetic data.
+"""Benchmark of the Poisson-GPFA EM hot path on B200 (BASELINE.json).
 
   python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU under torchrun)
   python bench.py --impl reference [--steps K --warmup W]    the reference algorithm on the host CPU
 
-A step is one EM iteration (E-step + M-step) of one fit; warm-up iterations are the first W
-iterations of the same fit (cold start included), the timed K iterations follow directly, i.e.
-steady-state warm-started EM.  One JSON line on stdout (rank 0).
+Headline (the JSON line's `value`): EM iterations / second of full-batch Laplace EM (E-step + M-step) on 1024 trials,
+q=8 latents, N=100 neurons, T=200 bins (BASELINE.json configs[2]), synthetic data.  A step is one EM iteration of one
+fit; warm-up iterations are the first W iterations of the same fit (cold start included), the timed K iterations follow
+directly, i.e. steady-state warm-started EM.  On one GPU the same line also carries (`config_results`) the variational
+E-step at the headline shape (configs[3]), stochastic mini-batch EM on 16384 trials of q=10/N=200/T=250 (configs[4]) and
+(`roofline_dense`) the batched dense qT x qT Cholesky the north star names.  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes
+import importlib.util
 import json
 import os
 import subprocess
@@ -24,17 +27,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(q=8, N=100, T=200, R=1024, binSize=10, dOffset=-1.0, seed=1)
+WORKLOAD_ONLINE = dict(q=10, N=200, T=250, R=16384, binSize=10, dOffset=-1.0, seed=1)
 METRIC = "EM iters/sec (Laplace E+M, 1024 trials q=8 T=200)"
 
 
+def _synth():
+    """poisson_gpfa_b200/_synth.py loaded by path: pure numpy, does not import the package (so the reference arm maps
+    no product library)."""
+    spec = importlib.util.spec_from_file_location("pgpfa_synth", os.path.join(ROOT, "poisson_gpfa_b200", "_synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_data(w, R=None):
-    from poisson_gpfa_b200 import util
+    syn = _synth()
     R = w["R"] if R is None else R
-    ex = util.simulate(w["seed"], w["q"], w["N"], R, w["T"], binSize=w["binSize"], dOffset=w["dOffset"])
+    ex = syn.simulate(w["seed"], w["q"], w["N"], R, w["T"], binSize=w["binSize"], dOffset=w["dOffset"])
     np.random.seed(123)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        ip = util.initializeParams(w["q"], w["N"], ex)
+        ip = syn.initializeParams(w["q"], w["N"], ex)
     ip = {k: np.ascontiguousarray(np.real(v), dtype=np.float64) for k, v in ip.items()}
     return ex, ip
 
@@ -89,6 +102,21 @@ class ClockSampler:
                 "samples_in_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only place where bench.py executes oracle/): the reference algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Let BLAS use every host core for the CPU legs.  torch.distributed.run exports OMP_NUM_THREADS=1 when it starts
+    more than one process; the reference arm (rank 0 only) must not inherit that."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def cpu_sample(w, R_cpu, warm, timed):
     """The reference algorithm (oracle dense port: same C_big / K_big formulation, same scipy optimisers and
     options as funs/inference.py + funs/learning.py, funs/engine.py:180-239 loop) on a bounded sample of the same
@@ -102,10 +130,46 @@ def cpu_sample(w, R_cpu, warm, timed):
     return float(per_it[warm:].mean()), out
 
 
+def cpu_ops_sample(w, variational):
+    """Bounded CPU sample for the configurations whose reference iteration takes hours per trial: the reference's inner
+    loop body (dense objective / gradient / Hessian of funs/inference.py:12-65, or the dual and its gradient,
+    :196-219) timed once each at the full shape on one trial, times the evaluation counts scipy made in the same
+    optimiser on a small instance of the same model (measured here too).  Extrapolated, and labelled so."""
+    from oracle import pgpfa_oracle as po
+    q, N, T = w["q"], w["N"], w["T"]
+    ex, ip = make_data(w, 1)
+    y = np.asarray(ex.data[0]['Y'], dtype=np.float64).reshape(-1)
+    C_big, d_big = po.make_Cd_big(ip, T)
+    K_big, K = po.make_K_big(ip, T * w["binSize"], w["binSize"])
+    K_bigInv = np.linalg.inv(K_big)
+    tick = time.perf_counter
+    if not variational:
+        x = np.zeros(q * T)
+        t0 = tick(); po.dense_nlp(x, y, C_big, d_big, K_bigInv); tf = tick() - t0
+        t0 = tick(); po.dense_nlp_grad(x, y, C_big, d_big, K_bigInv); tg = tick() - t0
+        t0 = tick(); H = po.dense_nlp_hess(x, y, C_big, d_big, K_bigInv); th = tick() - t0
+        t0 = tick(); np.linalg.inv(H); tinv = tick() - t0
+        # evaluation counts of scipy Newton-CG on a small instance (cold start, as the online rule always is)
+        sm = dict(w); sm.update(N=20, T=40)
+        exs, ips = make_data(sm, 2)
+        cnt = po.count_laplace_evals([np.asarray(t['Y'], dtype=np.float64) for t in exs.data], ips, sm["T"], sm["binSize"])
+        per_trial = cnt["nfev"] * tf + cnt["njev"] * tg + cnt["nhev"] * th + tinv
+        return per_trial, {"t_f": tf, "t_g": tg, "t_H": th, "t_inv": tinv, "evals_per_trial": cnt}
+    lam = np.full(N * T, 0.5)
+    t0 = tick(); po.dense_dual(lam, y, C_big, K_big, K_bigInv, d_big); tf = tick() - t0
+    t0 = tick(); po.dense_dual_grad(lam, y, C_big, K_big, K_bigInv, d_big); tg = tick() - t0
+    sm = dict(w); sm.update(N=10, T=20, q=2)
+    exs, ips = make_data(sm, 2)
+    cnt = po.count_dual_evals([np.asarray(t['Y'], dtype=np.float64) for t in exs.data], ips, sm["T"], sm["binSize"])
+    per_trial = cnt["funcalls"] * (tf + tg)
+    return per_trial, {"t_dual": tf, "t_dual_grad": tg, "evals_per_trial": cnt}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = host_threads()
     w = dict(WORKLOAD)
     R_cpu = args.cpu_trials
     sec, _ = cpu_sample(w, R_cpu, args.warmup_ref, args.steps)
@@ -115,13 +179,62 @@ def run_reference(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: synthetic q=8 N=100 T=200 R=1024 full-batch Laplace EM, steady-state "
                                    "(warm-started) iterations"},
-            "cpu_baseline": {"value": value, "unit": "EM iters/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": "%d warm-started EM iterations (dense C_big formulation, scipy Newton-CG/TNC/BFGS "
-                                       "at the reference's options) on %d of 1024 trials, %.1f s each; per-trial cost is "
-                                       "exactly linear in trials (serial loops funs/inference.py:94, "
-                                       "funs/learning.py:39), extrapolated x%d" % (args.steps, R_cpu, sec, w["R"] // R_cpu)},
+            "extrapolated": True,
+            "cpu_baseline": {"value": value, "unit": "EM iters/s", "cores": threads, "kind": "port",
+                             "sample": "EXTRAPOLATED: %d warm-started EM iterations (dense C_big formulation, scipy "
+                                       "Newton-CG/TNC/BFGS at the reference's options, BLAS on %d threads) on %d of 1024 "
+                                       "trials, %.1f s each; per-trial cost is exactly linear in trials (serial loops "
+                                       "funs/inference.py:94, funs/learning.py:39), x%d"
+                                       % (args.steps, threads, R_cpu, sec, w["R"] // R_cpu)},
             "e2e": {"value": value, "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def fp64_peak_live(torch):
+    """The FP64 roofline denominator measured in THIS process: cuBLAS DGEMM 8192^3 through torch.matmul (a library
+    call, used for measurement only), best of 5 single launches (burst) and a ~1 s back-to-back loop (sustained)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cnt, t0 = 0, time.time()
+    e0.record()
+    while time.time() - t0 < 1.0:
+        for _ in range(4):
+            torch.matmul(a, b); cnt += 1
+        torch.cuda.synchronize()
+    e1.record(); torch.cuda.synchronize()
+    del a, b
+    torch.cuda.empty_cache()
+    return {"burst_tflops": 2.0 * n ** 3 / best * 1e-9, "sustained_tflops": 2.0 * n ** 3 * cnt / e0.elapsed_time(e1) * 1e-9,
+            "how": "torch.matmul float64 8192^3 (cuBLAS DGEMM), best of 5 / 1 s back to back, CUDA events, this process"}
+
+
+def get_profile(_lib, h):
+    ms, work, cnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    _lib.call("pgpfa_get_profile", h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(work, ctypes.c_void_p),
+              ctypes.cast(cnt, ctypes.c_void_p))
+    return list(ms), list(work), list(cnt)
+
+
+def traffic_record(name):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        d["file"] = "profiles/" + name
+        return d
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -163,36 +276,34 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def em_iteration(params, x0):
-        newp, est, lik, info = trials.em_step(params, x0=x0)
-        return newp, est, lik, info["cd_iters"], info["tau_evals"]
-
     params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
     sampler = ClockSampler(dev_index)
     if rank == 0:
         sampler.start()                       # already sampling when the timed region begins
     x0, liks = None, []
     for _ in range(args.warmup):
-        params, est, lik, _, _ = em_iteration(params, x0)
+        params, est, lik, _ = trials.em_step(params, x0=x0)
         x0 = est.x
         liks.append(lik)
 
     # ---------------- timed region: K steady-state EM iterations, device-resident inputs
     _lib.call("pgpfa_set_profiling", h, 1)
     launches0 = _lib.lib.pgpfa_launch_count()
-    syncs0 = _lib.host_sync_count()
+    syncs0, thr0 = _lib.host_sync_count(), _lib.lib.pgpfa_throttle_wait_count(h)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.begin()
     e0.record()
-    newton_its, facts, cd_its, tau_evals, chord_its, fallback = [], 0, [], [], [], []
+    cd_its, tau_evals, newton_its, cg_its, ranks_seen = [], [], [], [], []
+    params_in = params
     for _ in range(args.steps):
-        params, est, lik, cd_it, nfev = em_iteration(params, x0)
+        params_in = params
+        params, est, lik, info = trials.em_step(params, x0=x0)
         x0 = est.x
         liks.append(lik)
-        newton_its.append(est.stats["max_newton_iters"]); facts += est.stats["factorizations"]
-        cd_its.append(cd_it); tau_evals.append(nfev)
-        chord_its.append(est.stats["pcg_newton_iters"]); fallback.append(est.stats["pcg_iters"])
+        cd_its.append(info["cd_iters"]); tau_evals.append(info["tau_evals"])
+        newton_its.append(est.stats["pcg_newton_iters"]); cg_its.append(est.stats["pcg_iters"])
+        ranks_seen.append(int(est.stats.get("lowrank_r", 0)))
     e1.record()
     barrier()
     sampler.end()
@@ -200,9 +311,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.lib.pgpfa_launch_count() - launches0
     host_syncs = _lib.host_sync_count() - syncs0
-    prof_ms, prof_work, prof_cnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
-    _lib.call("pgpfa_get_profile", h, ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_work, ctypes.c_void_p),
-              ctypes.cast(prof_cnt, ctypes.c_void_p))
+    throttle_waits = _lib.lib.pgpfa_throttle_wait_count(h) - thr0
+    prof_ms, prof_work, prof_cnt = get_profile(_lib, h)
     _lib.call("pgpfa_set_profiling", h, 0)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -210,11 +320,28 @@ def run_ours(args):
         ms = float(t.item())
     value = args.steps / (ms * 1e-3)
 
+    # ---------------- in-bench parity spot check: two trials of the LAST timed E-step against the oracle
+    spot = None
+    if rank == 0 and not args.profile_mode and not args.skip_cpu:
+        from oracle import pgpfa_oracle as po          # checker only
+        pin = params_in.to_numpy_dict()
+        sel = sorted({0, hi - lo - 1})
+        ys = [Y_host[lo + r] for r in sel]
+        ir, _, _, _ = po.laplace_struct(ys, pin, T, w["binSize"], want_cov=False)
+        rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+        xs = est.x[sel].cpu().numpy(); vs = est.vsm[sel].cpu().numpy()
+        spot = {"trials": sel, "post_mean": rel(xs, np.stack(ir['post_mean'])), "post_vsm": rel(vs, np.stack(ir['post_vsm'])),
+                "against": "oracle.laplace_struct (exact Newton to 1e-13 + dense inverse) on the parameters of the last timed step"}
+        if est.vsmGP is not None:
+            spot["post_vsmGP"] = rel(est.vsmGP[sel].cpu().numpy(), np.stack([v.transpose(2, 0, 1) for v in ir['post_vsmGP']]))
+
     # ---------------- e2e: the same EM iteration through the public API with HOST buffers every step
     e2e_steps = max(1, min(args.e2e_steps, args.steps)) if not args.profile_mode else 0
-    Y_pin = torch.from_numpy(Y_host).pin_memory()
+    counts_max = float(Y_host.max())
+    cdtype = torch.uint8 if counts_max <= 255 else (torch.int16 if counts_max <= 32767 else torch.float64)
+    Y_pin = torch.from_numpy(Y_host).to(cdtype).pin_memory()       # the counts as the host holds them (integers)
     host_params = params.to_numpy_dict()
-    modes_host = est.x.cpu().numpy()            # this rank's modes
+    prev = inference._TrialView(est.x.reshape(hi - lo, n)) if e2e_steps else None
     e2e_t = []
     h2d = d2h = 0
     exp = inference_experiment(Y_pin, w)
@@ -223,18 +350,15 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         inference.upload_counts(exp)                       # H2D of this step's inputs (pinned -> HBM)
-        prev = None
-        if modes_host is not None:                         # per-trial modes of the previous iteration, host side
-            prev = np.zeros((R, n))
-            prev[lo:hi] = modes_host.reshape(hi - lo, n)
-        infRes, lik_e, optim = inference.laplace(exp, host_params, prevOptimRes=prev, reducer=red)
-        host_params, det = learning.updateParams(host_params, infRes, exp)
-        modes_host = optim.tensor.cpu().numpy()            # D2H of the step's results
+        # parameters go in as host numpy; the warm start is the opaque lapOptimRes of the previous call, exactly how
+        # the reference threads it through (funs/engine.py:192-196) — here it is device-backed and never leaves HBM
+        infRes, lik_e, prev = inference.laplace(exp, host_params, prevOptimRes=prev, reducer=red)
+        host_params, det = learning.updateParams(host_params, infRes, exp)      # D2H of the step's results
         barrier()
         if i >= E2E_WARMUP:
             e2e_t.append(time.perf_counter() - t0)
-        h2d = (hi - lo) * N * T * 8 + (hi - lo) * n * 8 + (N * q + N + q) * 8
-        d2h = (hi - lo) * n * 8 + (N * q + N + q) * 8 + 8
+        h2d = (hi - lo) * N * T * Y_pin.element_size() + (N * q + N + q) * 8
+        d2h = (N * q + N + q) * 8 + 8 + 8
     e2e_sec = float(np.mean(e2e_t)) if e2e_t else float("nan")
     print("e2e step times (s):", [round(t, 4) for t in e2e_t], file=sys.stderr)
     if world > 1:
@@ -247,38 +371,34 @@ def run_ours(args):
             torch.distributed.barrier()
             torch.distributed.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
-    except Exception:
-        pass
-    fp64_peak = float(peaks.get("fp64_roofline_peak_tflops", 35.4))
-    lowrank_r = int(est.stats.get("lowrank_r", 0))
-    other = {"solves": prof_ms[1] / args.steps, "eval_linesearch": prof_ms[2] / args.steps,
+
+    # ---------------- roofline of the dominant kernel family of the timed region
+    peak_live = fp64_peak_live(torch) if not args.profile_mode else None
+    fp64_peak = peak_live["sustained_tflops"] if peak_live else 35.46
+    peak_src = ("cuBLAS DGEMM 8192^3 sustained, measured in this run (%s); MEASURED_PEAKS.json has no FP64 line"
+                % peak_live["how"]) if peak_live else "profiles/r01_fp64_peaks.json (35.46 TFLOP/s)"
+    lowrank_r = int(np.mean(ranks_seen)) if ranks_seen and min(ranks_seen) > 0 else 0
+    other = {"solves": prof_ms[1] / args.steps, "eval_cg_linesearch": prof_ms[2] / args.steps,
              "trtri": prof_ms[3] / args.steps, "cov_slices": prof_ms[4] / args.steps,
              "factor": prof_ms[0] / args.steps, "cg_preconditioner_setup": prof_ms[5] / args.steps,
              "lowrank_posterior_other": prof_ms[6] / args.steps}
-
-    def traffic_of(fname, key):
-        try:
-            return json.load(open(os.path.join(ROOT, "profiles", fname)))[key] * (hi - lo) / 1024.0   # captured at 1024 trials
-        except Exception:
-            return None
-
-    peak_src = ("measured cuBLAS DGEMM 8192^3 sustained on this pool (profiles/r01_fp64_peaks.json); "
-                "MEASURED_PEAKS.json has no FP64 line")
     if lowrank_r > 0:
-        # low-rank posterior pass (csrc/lowrank.cu): the dominant launch is the batched symmetric product
-        # post_vsmGP[k] = eps diag(P) + Y_k Y_k^T (gemm_nt_kernel, q x trials problems of T x T x r)
         k_ms, k_flops, k_cnt = prof_ms[4], prof_work[4], prof_cnt[4]
         achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        tr = traffic_record("r02_syrk_traffic.json") or traffic_record("r01_syrk_traffic.json")
+        traffic = None
+        if tr and "dram_bytes_per_launch" in tr:
+            traffic = (tr["dram_bytes_per_launch"] * (hi - lo) / float(tr.get("trials", 1024))
+                       * lowrank_r / float(tr.get("r", lowrank_r)))
         roofline = {"bound": "tensor",
-                    "kernel": "gemm_nt_kernel, the post_vsmGP launch (q*trials symmetric T x T x r products Y_k Y_k^T on DMMA.8x8x4); "
-                              "r = %d is the rank of the prior factor; the C,d M-step runs concurrently on a second stream" % lowrank_r,
+                    "kernel": "the post_vsmGP / PautoSum product of the low-rank posterior pass (q*trials symmetric T x T x r "
+                              "products Y_k Y_k^T on DMMA.8x8x4; mean r = %d of the prior factor over the timed steps); the "
+                              "C,d M-step runs concurrently on a second stream" % lowrank_r,
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                    "traffic": traffic_of("r01_syrk_traffic.json", "dram_bytes_per_launch"),
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full capture "
-                                      "(profiles/r01_syrk_traffic.json), scaled to this rank's trial count",
+                    "traffic": traffic,
+                    "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of that launch from an ncu --set full "
+                                       "capture (%s: r = %s, %s trials), scaled linearly to this run's mean r and trial count"
+                                       % (tr.get("file"), tr.get("r", "n/a"), tr.get("trials", 1024))) if tr else None,
                     "peak_source": peak_src,
                     "algorithmic_flops_per_launch": k_flops / max(k_cnt, 1), "launches": int(k_cnt),
                     "share_of_step": k_ms / ms, "other_ms_per_step": other,
@@ -288,28 +408,26 @@ def run_ours(args):
         achieved = fac_flops / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "batched Cholesky call (chol_diag_kernel + chol_panel_kernel launches, DMMA.8x8x4); a launch = one factorisation of all trials of the rank",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                    "traffic": traffic_of("r01_factor_traffic.json", "dram_bytes_per_factorisation"),
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one factorisation call, "
-                                      "ncu launch list of this command (profiles/r01_factor_traffic.json), scaled to this rank's "
-                                      "trial count",
-                    "peak_source": peak_src,
+                    "traffic": None, "peak_source": peak_src,
                     "algorithmic_flops_per_launch": fac_flops / max(fac_cnt, 1), "launches": int(fac_cnt),
                     "share_of_step": fac_ms / ms, "other_ms_per_step": other,
                     "trtri_tflops": prof_work[3] / (prof_ms[3] * 1e-3) / 1e12 if prof_ms[3] > 0 else None,
                     "solve_gbs": prof_work[1] / (prof_ms[1] * 1e-3) / 1e9 if prof_ms[1] > 0 else None}
+    extras_on = world == 1 and not args.profile_mode and not args.headline_only and not args.trials
     cpu = None
     if not args.skip_cpu and not args.profile_mode and world == 1:
+        threads = host_threads()
         sec, _ = cpu_sample(w, args.cpu_trials, 1, 1)
         v = 1.0 / (sec * R / args.cpu_trials)
-        cpu = {"value": v, "unit": "EM iters/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "second (warm-started) EM iteration of the dense reference formulation on %d of %d trials "
-                         "(%.1f s), linear extrapolation in trials" % (args.cpu_trials, R, sec)}
+        cpu = {"value": v, "unit": "EM iters/s", "cores": threads, "kind": "port",
+               "sample": "EXTRAPOLATED: second (warm-started) EM iteration of the dense reference formulation on %d of %d "
+                         "trials (%.1f s, BLAS on %d threads), linear extrapolation in trials" % (args.cpu_trials, R, sec, threads)}
     line = {"metric": METRIC, "value": value, "unit": "EM iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: synthetic q=8 N=100 T=200 R=%d full-batch Laplace EM, steady-state "
                                    "(warm-started) iterations" % R,
-                       "posterior_pass": ("low-rank prior factor, r=%d of qT=%d" % (lowrank_r, n)) if lowrank_r else "dense tiled Cholesky",
+                       "posterior_pass": ("low-rank prior factor, mean r=%d of qT=%d" % (lowrank_r, n)) if lowrank_r else "dense tiled Cholesky",
                        "trials_per_gpu": hi - lo,
                        "l2": ("working set (Y, post_vsmGP, counts: %.1f GB/GPU) >> L2, no flush needed"
                               % ((hi - lo) * (n * lowrank_r + q * T * T + N * T) * 8 / 1e9)) if lowrank_r else
@@ -318,11 +436,36 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": 1.0 / e2e_sec, "unit": "EM iters/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "inference.laplace + learning.updateParams with host numpy inputs/outputs each step"},
+                    "api": "inference.upload_counts (pinned host counts, %s) + inference.laplace + learning.updateParams with "
+                           "host numpy parameters in and out each step; the warm start is the previous call's lapOptimRes "
+                           "(device-backed)" % str(cdtype).replace("torch.", "")},
             "roofline": roofline, "cpu_baseline": cpu,
-            "detail": {"newton_iters_per_step": newton_its, "trial_factorisations": facts, "cd_newton_iters": cd_its,
-                       "tau_evals": tau_evals, "inexact_newton_iters_per_step": chord_its, "pcg_iters_per_step": fallback, "post_lik": liks[-3:], "allreduces": red.n_allreduce,
-                       "host_syncs_per_step": host_syncs / args.steps}}
+            "detail": {"cd_newton_iters": cd_its, "tau_evals": tau_evals, "inexact_newton_iters_per_step": newton_its,
+                       "pcg_iters_per_step": cg_its, "lowrank_r_per_step": ranks_seen, "post_lik": liks[-3:],
+                       "allreduces": red.n_allreduce,
+                       "host_syncs_per_step": host_syncs / args.steps,
+                       "host_syncs_are": "cudaStreamSynchronize + waits that empty the stream + device->host reads of the "
+                                         "Python layer; throttle waits (host ahead of the device by the loop depth, device "
+                                         "not idle) are counted separately",
+                       "throttle_waits_per_step": throttle_waits / args.steps,
+                       "parity_spot_check": spot, "fp64_peak_live": peak_live}}
+    del trials, est, x0
+    torch.cuda.empty_cache()
+    if extras_on:
+        extra = {}
+        for name, fn in (("configs[3]", run_variational), ("configs[4]", run_online)):
+            try:
+                extra[name] = fn(args, fp64_peak, peak_src)
+            except Exception as exc:        # an extra configuration must not take the headline line down with it
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                extra[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+        line["config_results"] = extra
+        try:
+            line["roofline_dense"] = run_dense_cholesky(fp64_peak, peak_src)
+        except Exception as exc:
+            line["roofline_dense"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -330,10 +473,177 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+def run_variational(args, fp64_peak, peak_src):
+    """BASELINE.json configs[3]: the headline shape with the dual variational E-step (funs/inference.py:259-432) and the
+    same M-step.  Every sweep of the E-step factorises the dense qT x qT posterior precision of every trial, so the
+    dominant kernel is the batched Cholesky."""
+    import torch
+    from poisson_gpfa_b200 import _lib, core
+    w = dict(WORKLOAD)
+    ex, ip = make_data(w)
+    q, N, T, R = w["q"], w["N"], w["T"], w["R"]
+    Y = np.stack([np.asarray(t['Y'], dtype=np.float64) for t in ex.data])
+    trials = core.DeviceTrials(_lib.dev_f64(Y), w["binSize"])
+    h = _lib.handle()
+    params = core.DeviceParams(ip['C'], ip['d'], ip['tau'], T, w["binSize"])
+    lam0, sweeps = None, []
+    warm, steps = 1, max(1, min(args.vi_steps, args.steps))
+    for _ in range(warm):
+        params, est, lik, info = trials.em_step(params, inference='variational', lam0=lam0)
+        lam0 = est.lam
+    _lib.call("pgpfa_set_profiling", h, 1)
+    n0, s0 = _lib.lib.pgpfa_launch_count(), _lib.host_sync_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        params, est, lik, info = trials.em_step(params, inference='variational', lam0=lam0)
+        lam0 = est.lam
+        sweeps.append(est.stats["sweeps"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    pm, pw, pc = get_profile(_lib, h)
+    _lib.call("pgpfa_set_profiling", h, 0)
+    n = q * T
+    out = {"workload": "configs[3]: synthetic q=8 N=100 T=200 R=1024, dual variational E-step + M-step, warm-started",
+           "metric": "EM iters/sec (variational E+M)", "value": steps / (ms * 1e-3), "unit": "EM iters/s", "steps": steps,
+           "warmup": warm, "ms_per_step": ms / steps, "sweeps_per_estep": sweeps, "post_lik": lik,
+           "gpu_launches": int(_lib.lib.pgpfa_launch_count() - n0), "host_syncs_per_step": (_lib.host_sync_count() - s0) / steps}
+    if pm[0] > 0:
+        ach = pw[0] / (pm[0] * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "batched dense Cholesky of the qT x qT variational precisions "
+                           "(chol_diag_kernel + chol_panel_kernel, DMMA.8x8x4)",
+                           "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                           "peak_source": peak_src, "algorithmic_flops": pw[0], "share_of_step": pm[0] / ms,
+                           "trtri_tflops": pw[3] / (pm[3] * 1e-3) / 1e12 if pm[3] > 0 else None}
+    if not args.skip_cpu:
+        threads = host_threads()
+        per_trial, det = cpu_ops_sample(w, variational=True)
+        out["cpu_baseline"] = {"value": 1.0 / (per_trial * R), "unit": "EM iters/s", "cores": threads, "kind": "port",
+                               "sample": "EXTRAPOLATED: one dualProblem + one dualProblem_grad evaluation of the dense "
+                                         "reference formulation at the full shape on 1 trial (%.1f s + %.1f s; the port takes "
+                                         "diag(C_big^T S C_big) without the reference's NT x NT product, i.e. it is faster than "
+                                         "funs/inference.py:218) x the L-BFGS-B evaluation count per trial measured on a "
+                                         "q=2,N=10,T=20 instance (%d) x 1024 trials; M-step not included"
+                                         % (det["t_dual"], det["t_dual_grad"], det["evals_per_trial"]["funcalls"])}
+    return out
+
+
+def run_online(args, fp64_peak, peak_src):
+    """BASELINE.json configs[4]: stochastic mini-batch EM (funs/engine.py:290-450, rule 'diag'), 16384 trials of q=10,
+    N=200, T=250 resident in HBM; every iteration draws a mini-batch (numpy RNG, host), runs a COLD-start Laplace
+    E-step on it (the reference never warm-starts online) and the proximal M-step."""
+    import torch
+    from poisson_gpfa_b200 import _lib, inference, learning, util
+    w = dict(WORKLOAD_ONLINE)
+    q, N, T, R = w["q"], w["N"], w["T"], w["R"]
+    ex = util.simulate_on_device(w["seed"], q, N, R, T, binSize=w["binSize"], dOffset=w["dOffset"],
+                                 tau=np.linspace(0.05, 0.3, q))
+    rng = np.random.RandomState(5)
+    ip = {'C': ex.params['C'] + 0.1 * rng.randn(N, q), 'd': ex.params['d'] + 0.1 * rng.randn(N),
+          'tau': ex.params['tau'] * 1.3}
+    h = _lib.handle()
+    res = {"workload": "configs[4]: synthetic q=10 N=200 T=250, 16384 trials resident, online EM rule 'diag', cold-start "
+                       "Laplace E-step per mini-batch (qT = 2500 posterior systems)",
+           "metric": "mini-batch EM iters/sec", "unit": "mini-batch EM iters/s"}
+    stepPow = 0.75
+    for B in (512, 5):
+        np.random.seed(7)
+        params = {k: v.copy() for k, v in ip.items()}
+        warm, steps = 2, max(2, min(args.online_steps, args.steps))
+        liks, rr = [], []
+        inv_prior = np.eye(q * N + N)
+        _lib.call("pgpfa_set_profiling", h, 1 if B == 512 else 0)
+        for it in range(warm + steps):
+            if it == warm:
+                torch.cuda.synchronize()
+                n0, s0 = _lib.lib.pgpfa_launch_count(), _lib.host_sync_count()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                t0 = time.perf_counter()
+            sub = util.subsampleTrials(ex, B)
+            infRes, lik, _ = inference.laplace(sub, params)
+            step = 1.0 / (it + 1) ** stepPow
+            params, det, inv_prior = learning.updateParamsWithPrior(params, infRes, sub, 'TNC', 'TNC', step, step, inv_prior,
+                                                                    covOpts='useDiag')
+            liks.append(lik); rr.append(int(infRes.device.stats.get("lowrank_r", 0)))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        key = "batch%d" % B
+        res[key] = {"value": steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "warmup": warm,
+                    "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps, "post_lik_last": liks[-1],
+                    "lowrank_r": rr[-1], "gpu_launches": int(_lib.lib.pgpfa_launch_count() - n0),
+                    "host_syncs_per_step": (_lib.host_sync_count() - s0) / steps}
+        if B == 512:
+            pm, pw, pc = get_profile(_lib, h)
+            _lib.call("pgpfa_set_profiling", h, 0)
+            if pm[4] > 0:
+                ach = pw[4] / (pm[4] * 1e-3) / 1e12
+                res[key]["roofline"] = {"bound": "tensor", "kernel": "post_vsmGP product of the low-rank pass (as in the headline)",
+                                        "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                                        "traffic": None, "peak_source": peak_src}
+    res["value"] = res["batch512"]["value"]
+    if not args.skip_cpu:
+        threads = host_threads()
+        per_trial, det = cpu_ops_sample(w, variational=False)
+        res["cpu_baseline"] = {"value": 1.0 / (per_trial * 5), "unit": "mini-batch EM iters/s (batchSize 5)", "cores": threads,
+                               "kind": "port",
+                               "sample": "EXTRAPOLATED: one dense objective / gradient / Hessian evaluation and one inverse of "
+                                         "the reference formulation at q=10,N=200,T=250 on 1 trial (%.2f / %.2f / %.1f / %.1f s) x "
+                                         "scipy Newton-CG's evaluation counts per cold-start trial measured on a N=20,T=40 "
+                                         "instance (f %d, g %d, H %d) x the 5 trials of a reference mini-batch; M-step not "
+                                         "included" % (det["t_f"], det["t_g"], det["t_H"], det["t_inv"],
+                                                       det["evals_per_trial"]["nfev"], det["evals_per_trial"]["njev"],
+                                                       det["evals_per_trial"]["nhev"])}
+    return res
+
+
+def run_dense_cholesky(fp64_peak, peak_src):
+    """The batched blocked FP64 Cholesky of the north star (funs/inference.py:130-131 inverts these matrices): all 1024
+    posterior Hessians H = blkdiag(K^-1) + scatter(W) of the headline shape (qT = 1600), generated on the fly, factored
+    by pgpfa_potrf_posterior; timed alone with CUDA events."""
+    import torch
+    from poisson_gpfa_b200 import _lib, kernels as kn, core
+    w = dict(WORKLOAD)
+    q, N, T, R = w["q"], w["N"], w["T"], w["R"]
+    n = q * T
+    rng = np.random.RandomState(2)
+    tau = _lib.dev_f64(np.linspace(0.05, 0.3, q))
+    K = kn.make_K(tau, T, w["binSize"], core.EPS_NOISE)
+    Kinv, _, _ = kn.spd_inverse(K)
+    # W: per-bin q x q SPD blocks of the size the E-step produces (C^T diag(rate) C)
+    Cm = rng.rand(N, q) - 0.5
+    lam = np.exp(-1.0 + 0.3 * rng.randn(8, N, T))
+    Wsmall = np.einsum('nk,nl,rnt->rklt', Cm, Cm, lam).reshape(8, q * q, T)
+    W = _lib.dev_f64(np.tile(Wsmall, (R // 8, 1, 1)))
+    bufs = kn.tile_buffers(R, n, want_zt=False)
+    times = []
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        L, D, ZT, info = kn.potrf_posterior(Kinv, W, 1.0, want_zt=False, bufs=bufs)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    assert int(info.abs().max()) == 0
+    t = min(times[1:])
+    flops = R * n * float(n) * n / 3.0
+    ach = flops / (t * 1e-3) / 1e12
+    tr = traffic_record("r01_factor_traffic.json")
+    return {"bound": "tensor", "kernel": "pgpfa_potrf_posterior: batched blocked Cholesky of 1024 x (1600 x 1600) FP64 systems "
+            "(chol_diag_kernel + chol_panel_kernel, 64x64 tiles, DMMA.8x8x4, UBLKCP-staged operands)",
+            "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "ms": t, "ms_all": times,
+            "algorithmic_flops": flops, "peak_source": peak_src,
+            "traffic": tr.get("dram_bytes_per_factorisation") if tr else None,
+            "traffic_source": "ncu launch list of round 1 (profiles/r01_factor_traffic.json), same shape and trial count" if tr else None,
+            "l2": "factor tiles 10.65 GB >> L2"}
+
+
 def inference_experiment(Y_pin, w):
     """A duck-typed experiment over pinned host counts (re-uploaded by the API on every e2e step)."""
-    from poisson_gpfa_b200 import util
-
     class _E:
         pass
     e = _E()
@@ -354,7 +664,10 @@ def main():
     ap.add_argument("--trials", type=int, default=0, help="override the trial count (debug only)")
     ap.add_argument("--cpu-trials", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--vi-steps", type=int, default=2)
+    ap.add_argument("--online-steps", type=int, default=10)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip configs[3], configs[4] and the dense Cholesky leg")
     ap.add_argument("--profile-mode", action="store_true", help="timed loop only (for runs under ncu)")
     args = ap.parse_args()
     if args.steps is None:

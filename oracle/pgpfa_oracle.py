@@ -440,6 +440,40 @@ def dense_dual_variational(experiment, params, optimizeLogLambda=False, prevOpti
     return res, -tot_lik / R, tot_lb / R, optim
 
 
+def count_laplace_evals(ys, params, T, binSize):
+    """Mean number of objective / gradient / Hessian evaluations scipy Newton-CG makes per trial in the reference's
+    E-step (funs/inference.py:119-126, cold start, default options).  bench.py multiplies them with the cost of one
+    evaluation at a shape where a whole reference E-step would take minutes per trial (labelled as an extrapolation)."""
+    N = ys[0].shape[0]
+    q = params['C'].shape[1]
+    C_big, d_big = make_Cd_big(params, T)
+    K_big, _ = make_K_big(params, T * binSize, binSize)
+    K_bigInv = np.linalg.inv(K_big)
+    tot = {"nfev": 0, "njev": 0, "nhev": 0}
+    for y in ys:
+        out = sopt.minimize(dense_nlp, np.zeros(q * T), args=(y.reshape(N * T), C_big, d_big, K_bigInv), method='Newton-CG',
+                            jac=dense_nlp_grad, hess=dense_nlp_hess, options={'disp': False, 'maxiter': 10000})
+        for k in tot:
+            tot[k] += int(getattr(out, k))
+    return {k: int(round(v / len(ys))) for k, v in tot.items()}
+
+
+def count_dual_evals(ys, params, T, binSize):
+    """Mean number of dual function(+gradient) evaluations L-BFGS-B makes per trial in the reference's variational E-step
+    (funs/inference.py:316-324, cold start lambda = 0.5, factr = 1e7)."""
+    N = ys[0].shape[0]
+    C_big, d_big = make_Cd_big(params, T)
+    K_big, _ = make_K_big(params, T * binSize, binSize)
+    K_bigInv = np.linalg.inv(K_big)
+    calls = 0
+    for y in ys:
+        out = sopt.fmin_l_bfgs_b(dense_dual, np.zeros(N * T) + 0.5, fprime=dense_dual_grad,
+                                 args=(y.reshape(N * T), C_big, K_big, K_bigInv, d_big),
+                                 bounds=[(1e-10, None)] * (N * T), factr=1e7)
+        calls += int(out[2]['funcalls'])
+    return {"funcalls": int(round(calls / len(ys)))}
+
+
 # ----------------------------------------------------------------------------
 # M-step: observation parameters C, d
 # ----------------------------------------------------------------------------

@@ -465,13 +465,16 @@ class DeviceTrials:
         return tau, ts.details()
 
     # ------------------------------------------------------------------ one device-resident EM iteration
-    def em_step(self, params, x0=None, tol=1e-8, cd_tol=1e-10, tau_xtol=1e-10):
+    def em_step(self, params, x0=None, tol=1e-8, cd_tol=1e-10, tau_xtol=1e-10, inference='laplace', lam0=None):
         """One full batch EM iteration (funs/engine.py:180-239: Laplace E-step, C,d M-step, timescale M-step) with the
         iteration loops driven from the device.  Host synchronisations: one wait inside the E-step driver (the number of
         trials that need the exact-Newton fallback decides what is enqueued next) and ONE packed read at the end
         (M-step flags, objective, error codes, and — for the next iteration's prior, already enqueued — positive
         definiteness and the low-rank ranks).  Returns (new DeviceParams, EStepResult, post_lik, info dict)."""
-        est = self.estep_laplace(params, x0=x0, tol=tol)
+        if inference == 'laplace':
+            est = self.estep_laplace(params, x0=x0, tol=tol)
+        else:       # dual variational E-step (funs/engine.py:202-209): same M-step on the variational posterior
+            est = self.estep_variational(params, lam0=lam0)
         cd = self.mstep_cd_async(params, est, tol=cd_tol)
         Psum = self.pautosum(est)
         ts = self.mstep_tau_async(params, Psum, xtol=tau_xtol)
@@ -482,7 +485,7 @@ class DeviceTrials:
         cd.join()
         vals = read_packed(pend_cd + pend_ts + pend_p)
         v_cd, v_ts, v_p = vals[:len(pend_cd)], vals[len(pend_cd):len(pend_cd) + len(pend_ts)], vals[len(pend_cd) + len(pend_ts):]
-        EStepResult.raise_on(v_cd[2])
+        EStepResult.raise_on(v_cd[2], "Laplace" if inference == 'laplace' else "variational")
         est._checked = True
         redo = v_cd[0][0] > 0 or v_ts[0][0] > 0
         C, d, cost, cd_it, _ = cd.finish(v_cd)

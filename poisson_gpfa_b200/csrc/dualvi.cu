@@ -355,19 +355,26 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
         for (int it = 0; it < max_iter && n_act > 0; it++) {
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, x, w.Kx, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_laplace_eval(x, w.Kx, y, C, d, act, n_act, q, N, T, w.fcur, w.g, w.W, st, s));
+            pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
             PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, act, info, n_act, st, h));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_FACTOR] += (double)n_act * n * (double)n * n / 3.0;
             total_factor += n_act;
             PGPFA_TRY(pgpfa_i_solve(w.L, w.Dinv, w.g, w.dx, -1.0, act, n, n_act, st));
             PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, n_act, q, T, st));
             PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, n_act, q, N, T, tol, w.fcur, w.conv,
                                          niter, w.steplen, -1, st, s));
+            pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);
             PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, n_act, st, h));
+            pgpfa_prof_end(h, st);
+            h->prof_work[PGPFA_PROF_TRTRI] += (double)n_act * n * (double)n * n / 3.0;
             PGPFA_TRY(pgpfa_i_timediag(w.ZT, act, vsm, n, q, T, n_act, st));
             VI_DISPATCH(vi_s_update_kernel, n_act, (size_t)N * q * sizeof(double), vsm, C, s, act, N, T, tol, w.conv, w.dsmax)
             PGPFA_TRY(pgpfa_i_compact(act, n_act, w.conv, 1, act_next, w.cnt, st));
             PGPFA_CUDA_TRY(cudaMemcpyAsync(h->pinned, w.cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
             PGPFA_TRY(pgpfa_sync(h, st));
             n_act = h->pinned[0];
+            pgpfa_prof_resolve(h);
             int *tmp = act; act = act_next; act_next = tmp;
             if (it + 1 > sweeps) sweeps = it + 1;
         }
@@ -376,12 +383,18 @@ extern "C" int pgpfa_dualvi_solve(pgpfa_handle_t h, const double *y, const doubl
         PGPFA_TRY(pgpfa_i_iota(w.actA, cn, c0, st));
         VI_DISPATCH(vi_rates_kernel, cn, smem_cd(N, q), x, s, nullptr, y, C, d, w.actA, N, T, 0, lam, w.v, w.W, w.sums)
         PGPFA_TRY(pgpfa_i_prior_apply(K, w.v, w.Kv, w.actA, cn, q, T, st));
+        pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
         PGPFA_TRY(pgpfa_i_factor(ms, w.L, w.Dinv, w.ZT, w.actA, info, cn, st, h));
+        pgpfa_prof_end(h, st);
+        h->prof_work[PGPFA_PROF_FACTOR] += (double)cn * n * (double)n * n / 3.0;
         total_factor += cn;
         PGPFA_TRY(pgpfa_i_logdet(w.L, n, cn, w.logdet, st));
         vi_dual_value_kernel<<<cn, 256, 0, st>>>(w.v, w.Kv, w.sums, w.logdet, w.actA, n, D, mean);
         PGPFA_LAUNCH_CHECK();
+        pgpfa_prof_begin(h, PGPFA_PROF_TRTRI, st);
         PGPFA_TRY(pgpfa_i_trtri(w.L, w.Dinv, w.ZT, n, cn, st, h));
+        pgpfa_prof_end(h, st);
+        h->prof_work[PGPFA_PROF_TRTRI] += (double)cn * n * (double)n * n / 3.0;
         PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
         if (vsmGP || cov_dense)
             PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, vsmGP,

@@ -36,10 +36,18 @@ def _full_counts(experiment):
     object.  Only needed for parents of mini-batches (util.subsampleTrials), which are gathered on the device."""
     cached = experiment.__dict__.get('_pgpfa_y')
     if cached is None or cached[1] is not experiment.data:
-        y = _host_rows(experiment, 0, len(experiment.data)).to(device="cuda", dtype=torch.float64).contiguous()
+        y = _to_device_f64(_host_rows(experiment, 0, len(experiment.data)))
         cached = (y, experiment.data)
         experiment.__dict__['_pgpfa_y'] = cached
     return cached[0]
+
+
+def _to_device_f64(rows):
+    """Host rows (any numeric dtype; pinned or pageable) -> float64 on the device.  Integer counts travel in their own
+    (compact) dtype and are widened on the device: the reference promotes counts to float64 on use as well."""
+    if rows.dtype == torch.float64:
+        return rows.to(device="cuda", non_blocking=True).contiguous()
+    return rows.to(device="cuda", non_blocking=True).to(torch.float64).contiguous()
 
 
 def upload_counts(experiment):
@@ -47,7 +55,11 @@ def upload_counts(experiment):
     dt = experiment.__dict__.get('_pgpfa_dev')
     if dt is None:
         return device_trials(experiment).y
-    dt.y.copy_(_host_rows(experiment, dt.offset, dt.offset + dt.R), non_blocking=True)
+    rows = _host_rows(experiment, dt.offset, dt.offset + dt.R)
+    if rows.dtype == torch.float64:
+        dt.y.copy_(rows, non_blocking=True)
+    else:
+        dt.y.copy_(rows.to(device="cuda", non_blocking=True))        # H2D in the compact dtype, widened on the device
     return dt.y
 
 
@@ -69,7 +81,7 @@ def device_trials(experiment, reducer=None):
         idx = torch.as_tensor(np.asarray(experiment.batchTrIdx)[lo:hi], device="cuda", dtype=torch.long)
         y = _full_counts(parent).index_select(0, idx).contiguous()
     else:
-        y = _host_rows(experiment, lo, hi).to(device="cuda", dtype=torch.float64).contiguous()
+        y = _to_device_f64(_host_rows(experiment, lo, hi))
     if parent is not None and hasattr(experiment, 'batchTrIdx') and y.shape[0] == 0:
         y = y.reshape(0, *_full_counts(parent).shape[1:])
     dt = DeviceTrials(y, experiment.binSize, reducer, R_total=R, offset=lo)
