@@ -139,12 +139,15 @@ int pgpfa_prior_lowrank(const double *K, int q, int T, double eps, double delta,
  * L_b L_b^T = I + F^T (W P) F (r x r, r = sum of the ranks), Sigma = eps P + Y Y^T exactly, so post_vsm / post_vsmGP
  * and the polishing Newton step need no qT x qT factorisation.  Same outputs as pgpfa_laplace_solve to the
  * truncation level delta (no dense covariance output).  rank_host: q ints on the HOST.  Falls back to the dense tiled
- * path when the scratch for rank r does not fit into the workspace's factor area.  stats_out[6] = r when it ran. */
+ * path when the scratch for rank r does not fit into the workspace's factor area.  stats_out[6] = r when it ran.
+ * pautosum (q,T,T), optional: sum over the R trials of post_vsmGP[k] + m_k m_k^T (makePrecomp, funs/learning.py:162-165)
+ * computed inside the pass as ONE symmetric product per latent over all trials; with vsmGP = NULL the per-trial T x T
+ * blocks are then never written (the EM loop only consumes their sum). */
 int pgpfa_laplace_solve_lowrank(pgpfa_handle_t h, const double *y, const double *C, const double *d, const double *Kinv,
                                 const double *F, const double *Ft, const int *rank_host, double eps, double *x, int R,
                                 int q, int N, int T, double tol, int max_newton, int flags, double *f_out, double *vsm,
-                                double *vsmGP, int *niter, int *info, void *workspace, long long ws_bytes,
-                                int *stats_out, cudaStream_t stream);
+                                double *vsmGP, double *pautosum, int *niter, int *info, void *workspace,
+                                long long ws_bytes, int *stats_out, cudaStream_t stream);
 
 /* Leave-one-neuron-out prediction, funs/engine.py:599-644: problem p = (trial ymap[p], left-out neuron excl[p]);
  * the posterior mode is found without that neuron (x: P x q x T, in = start, out = mode) and its rate predicted:

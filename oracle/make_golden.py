@@ -107,8 +107,12 @@ def online_case(ref, name, ds, ip, n_iter, batchSize, method):
     out['seed'] = 2024
     if method in ('hess', 'diag'):
         out['invPriorCov_last'] = fit.invPriorCovs[-1]
+        # iteration 1 of 'hess': minus the reference's finite-difference Jacobian (funs/util.py:377-434) of the prior-cost
+        # gradient at the initial parameters (funs/learning.py:545-549) — the function-level pin of the analytic blocks
+        out['invPriorCov_1'] = fit.invPriorCovs[1]
     if method == 'grad':
         out['cumHess_last'] = fit.cumHess[-1]
+        out['cumHess_1'] = fit.cumHess[1]          # I + the FD Hessian of the first mini-batch (funs/learning.py:884-891)
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print(name, 'written')
 
@@ -159,10 +163,16 @@ def main():
         ds = ref.util.dataset(seed=np.random.randint(10000), xdim=2, ydim=20, numTrials=5, trialDur=1000, binSize=20,
                               dOffset=1, fixTau=True, fixedTau=np.linspace(0.1, 0.5, 2), drawSameX=True)
         ip = ref.util.initializeParams(2, 20, ds)
-    em_case(ref, 'example_laplace', ds, ip, 3, 2, 20, 50)
-    online_case(ref, 'example_online_diag', ds, ip, 4, 3, 'diag')
-    online_case(ref, 'example_online_hess', ds, ip, 3, 3, 'hess')
-    online_case(ref, 'example_online_grad', ds, ip, 3, 3, 'grad')
+    only = [a.split('=', 1)[1].split(',') for a in sys.argv if a.startswith('--only=')]
+    only = only[0] if only else None              # e.g. --only=example_online_hess,example_online_grad
+    want = lambda name: only is None or name in only
+    if want('example_laplace'):
+        em_case(ref, 'example_laplace', ds, ip, 3, 2, 20, 50)
+    for nm, it_, meth in (('example_online_diag', 4, 'diag'), ('example_online_hess', 3, 'hess'), ('example_online_grad', 3, 'grad')):
+        if want(nm):
+            online_case(ref, nm, ds, ip, it_, 3, meth)
+    if only is not None:
+        return
     # small ragged-ish shape: q=3, N=7 (few neurons), T=40, tile-unaligned n=120
     np.random.seed(5)
     with rh.quiet():

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpgpfa_b200.so")
+# PGPFA_LIB: development switch for A/B builds of the library (kernel variants under ncu); never set in tests / bench
+LIB_PATH = os.environ.get("PGPFA_LIB") or os.path.join(_HERE, "csrc", "libpgpfa_b200.so")
 
 c_int, c_ll, c_dbl, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
 P = c_void_p  # device pointers and streams travel as integers
@@ -29,7 +30,7 @@ SIGNATURES = {
     "pgpfa_stream_wait_means": (c_int, [c_void_p, c_void_p]),
     "pgpfa_prior_lowrank": (c_int, [P, c_int, c_int, c_dbl, c_dbl, P, P, P, P]),
     "pgpfa_laplace_solve_lowrank": (c_int, [c_void_p, P, P, P, P, P, P, P, c_dbl, P, c_int, c_int, c_int, c_int, c_dbl, c_int,
-                                            c_int, P, P, P, P, P, P, c_ll, P, P]),
+                                            c_int, P, P, P, P, P, P, P, c_ll, P, P]),
     "pgpfa_set_profiling": (c_int, [c_void_p, c_int]),
     "pgpfa_get_profile": (c_int, [c_void_p, P, P, P]),
     "pgpfa_map": (c_int, [c_int, c_ll, P, P, c_dbl, P, P]),

@@ -130,6 +130,22 @@ class EStepResult:
         self.params, self.trials = params, trials
         self.side = None      # stream on which x / f / vsm are complete while vsmGP may still be in flight on the main one
         self._checked = False
+        self.pautosum = None  # (q,T,T) local trial-sum of post_vsmGP + m m^T when the E-step produced it directly
+        self.tol = 1e-8
+
+    def get_vsmGP(self):
+        """post_vsmGP (R,q,T,T).  The EM loop only consumes the trial-sum (PautoSum), which the low-rank pass produces
+        directly; the per-trial T x T blocks are materialised on first access by one more posterior pass at the stored
+        mode (a converged start: one evaluation, no further Newton step)."""
+        if self.vsmGP is None and self.x is not None and self.x.shape[0] > 0:
+            p, t = self.params, self.trials
+            res = kn.laplace_solve(t.y, p.C, p.d, p.Kinv, x0=self.x, tol=self.tol, want_vsm=False, want_vsmGP=True,
+                                   lowrank=p.lowrank)
+            self.vsmGP = res.vsmGP
+        elif self.vsmGP is None and self.x is not None:
+            q, T = self.params.q, self.trials.T
+            self.vsmGP = torch.zeros(0, q, T, T, dtype=torch.float64, device="cuda")
+        return self.vsmGP
 
     def means_stream(self):
         """Context in which work that needs only x, f and vsm runs: the side stream if the E-step left one."""
@@ -263,7 +279,8 @@ class DeviceTrials:
         return side
 
     # ------------------------------------------------------------------ E-step
-    def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True):
+    def estep_laplace(self, params, x0=None, tol=1e-8, max_newton=60, want_vsmGP=True, inexact_newton=True,
+                      want_pautosum=False):
         """Batched Laplace E-step.  `tol` bounds the last Newton step (relative, inf-norm); the returned mode is one
         polishing Newton step closer (~1e-13 measured), the covariances are those at the point before that step
         (within ~4e-11 of the converged ones at tol = 1e-8, tools/parity_report.py)."""
@@ -282,8 +299,10 @@ class DeviceTrials:
             self._lap_ws = ((R, q, T), _lib.workspace(nbytes))
         res = kn.laplace_solve(self.y, params.C, params.d, params.Kinv, x0=x0, tol=tol, max_newton=max_newton,
                                want_vsm=True, want_vsmGP=want_vsmGP, ws=self._lap_ws[1], inexact_newton=inexact_newton,
-                               lowrank=params.lowrank)
-        est = EStepResult(res.x, res.f, res.vsm, res.vsmGP, res.niter, res.stats, params, self, info=res.info)
+                               lowrank=params.lowrank, want_pautosum=want_pautosum)
+        est = EStepResult(res.x, res.f, res.vsm, res.vsmGP if want_vsmGP else None, res.niter, res.stats, params, self,
+                          info=res.info)
+        est.pautosum, est.tol = res.pautosum, tol
         est.side = self._means_stream()
         return est
 
@@ -423,8 +442,12 @@ class DeviceTrials:
 
     # ------------------------------------------------------------------ M-step tau
     def pautosum(self, est):
-        if self.R > 0:
-            P = kn.pautosum(est.vsmGP, est.x)
+        """PautoSum over ALL trials (makePrecomp, funs/learning.py:145-173): this rank's sum — taken inside the low-rank
+        posterior pass when the E-step was asked for it, else over the per-trial blocks — all-reduced over the ranks."""
+        if getattr(est, "pautosum", None) is not None:
+            P = est.pautosum.clone()
+        elif self.R > 0:
+            P = kn.pautosum(est.get_vsmGP() if hasattr(est, "get_vsmGP") else est.vsmGP, est.x)
         else:
             P = torch.zeros(est.params.q, self.T, self.T, dtype=torch.float64, device="cuda")
         return self.reducer.sum_tensor(P)
@@ -472,7 +495,7 @@ class DeviceTrials:
         (M-step flags, objective, error codes, and — for the next iteration's prior, already enqueued — positive
         definiteness and the low-rank ranks).  Returns (new DeviceParams, EStepResult, post_lik, info dict)."""
         if inference == 'laplace':
-            est = self.estep_laplace(params, x0=x0, tol=tol)
+            est = self.estep_laplace(params, x0=x0, tol=tol, want_vsmGP=False, want_pautosum=True)
         else:       # dual variational E-step (funs/engine.py:202-209): same M-step on the variational posterior
             est = self.estep_variational(params, lam0=lam0)
         cd = self.mstep_cd_async(params, est, tol=cd_tol)

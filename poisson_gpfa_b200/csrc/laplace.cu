@@ -673,6 +673,7 @@ namespace {
 struct LapWs {
     double *Kx, *Kd, *g, *dx, *W, *fcur, *steplen, *pr, *pz, *pp, *pHp, *pcg_s;
     int *conv, *actA, *actB, *actC, *lslot, *cnt, *pinfo;
+    double *pauto_partial;                  // partial tiles of the PautoSum product (lowrank.cu)
     double *Mk, *Minv, *wbar, *plogdet;     // shared CG preconditioner: (Kinv_k + wbar_k I)^-1, one T x T matrix per latent
     void *pws;
     long long pws_bytes;
@@ -693,6 +694,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += 5 * align_up((size_t)R * 4) + 256;
     b += 2 * align_up((size_t)q * T * T * 8) + 2 * align_up((size_t)q * 8) + align_up((size_t)q * WD_PARTS * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
     b += align_up((size_t)npairs_max * sizeof(int2)) + align_up(PGPFA_LOWRANK_TABLE_BYTES);
+    b += align_up(pgpfa_i_pautosum_partial_bytes(q, T));
     return b;
 }
 size_t lap_per_trial_bytes(int q, int T) {
@@ -713,7 +715,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                               int max_newton, int flags, double *f_out, double *vsm, double *vsmGP,
                               double *cov_dense, int *niter, int *info, void *workspace, long long ws_bytes,
                               int *stats_out, cudaStream_t st, LooMap loo, bool posterior_pass,
-                              const PgpfaLowRank *lr = nullptr) {
+                              const PgpfaLowRank *lr = nullptr, double *pautosum = nullptr) {
     if (!h || !y || !C || !d || !Kinv || !x || !f_out || !niter || !info || !workspace) return PGPFA_ERR_ARG;
     if (R <= 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0 || max_newton <= 0) return PGPFA_ERR_ARG;
     const int n = q * T, nb = pgpfa_nb(n);
@@ -739,6 +741,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.cnt = (int *)take(256);
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
     w.lr_tables = take(PGPFA_LOWRANK_TABLE_BYTES);
+    w.pauto_partial = (double *)take(pgpfa_i_pautosum_partial_bytes(q, T));
     w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)q * T * T * 8);
     w.wbar = (double *)take((size_t)q * WD_PARTS * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
     w.pws_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
@@ -758,6 +761,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     bool use_lr = lr && lr->r > 0 && posterior_pass && !cov_dense &&
                   pgpfa_i_lowrank_bytes_per_slot(q, T, lr->r) <= per;
     if (use_lr) PGPFA_TRY(pgpfa_i_lowrank_prepare(h, *lr, q, T, w.lr_tables, st));
+    if (pautosum && !use_lr && !vsmGP) return PGPFA_ERR_ARG;     // the dense path sums the per-trial blocks it is given
     const int npairs = pgpfa_i_num_pairs(q, T, cov_dense != nullptr);
     PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, cov_dense != nullptr, st));
 
@@ -972,7 +976,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         pgpfa_prof_end(h, st);
         if (posterior_pass && use_lr) {
             PGPFA_TRY(pgpfa_i_lowrank_posterior(h, *lr, w.W, w.g, x, w.dx, w.actA, cn, q, T, tol, w.steplen, vsm, vsmGP,
-                                                w.L, w.lr_tables, st, info));
+                                                w.L, w.lr_tables, st, info, pautosum, c0 > 0 ? 1 : 0, x, w.pauto_partial));
             total_factor_trials += cn;
         } else if (posterior_pass) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);
@@ -998,6 +1002,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             if (vsmGP || cov_dense)
                 PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, vsmGP,
                                         cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
+            if (pautosum)
+                PGPFA_TRY(pgpfa_i_pautosum(vsmGP + (size_t)c0 * q * T * T, x + (size_t)c0 * n, cn, q, T, c0 > 0 ? 1 : 0, pautosum, st));
             pgpfa_prof_end(h, st);
         }
     }
@@ -1028,8 +1034,8 @@ extern "C" int pgpfa_laplace_solve(pgpfa_handle_t h, const double *y, const doub
 extern "C" int pgpfa_laplace_solve_lowrank(pgpfa_handle_t h, const double *y, const double *C, const double *d,
                                            const double *Kinv, const double *F, const double *Ft, const int *rank_host,
                                            double eps, double *x, int R, int q, int N, int T, double tol, int max_newton,
-                                           int flags, double *f_out, double *vsm, double *vsmGP, int *niter, int *info,
-                                           void *workspace, long long ws_bytes, int *stats_out, cudaStream_t st) {
+                                           int flags, double *f_out, double *vsm, double *vsmGP, double *pautosum, int *niter,
+                                           int *info, void *workspace, long long ws_bytes, int *stats_out, cudaStream_t st) {
     if (!F || !Ft || !rank_host || q <= 0 || q > PGPFA_QMAX || !(eps > 0.0)) return PGPFA_ERR_ARG;
     PgpfaLowRank lr;
     lr.F = F; lr.Ft = Ft; lr.eps = eps; lr.r = 0;
@@ -1043,7 +1049,7 @@ extern "C" int pgpfa_laplace_solve_lowrank(pgpfa_handle_t h, const double *y, co
     LooMap loo;
     loo.ymap = nullptr; loo.excl = nullptr;
     return laplace_solve_impl(h, y, C, d, Kinv, x, R, q, N, T, tol, max_newton, flags, f_out, vsm, vsmGP, nullptr,
-                              niter, info, workspace, ws_bytes, stats_out, st, loo, true, &lr);
+                              niter, info, workspace, ws_bytes, stats_out, st, loo, true, &lr, pautosum);
 }
 
 // y_pred[p][t] = exp(c_n . x_p[:,t] + d_n) for the left-out neuron n = excl[p]; err[p] = sum_t (y - y_pred)^2

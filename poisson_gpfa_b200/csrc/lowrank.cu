@@ -18,6 +18,7 @@
 // (DMMA.8x8x4); the r x r factorisation and triangular inverse are the tile kernels of factor.cu.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "pgpfa_internal.h"
@@ -297,6 +298,268 @@ __global__ void __launch_bounds__(128, 3) gemm_nt_kernel(GemmArgs g) {
             }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PautoSum through the low-rank factor (funs/learning.py:162-165): the timescale M-step only consumes
+//     PautoSum[k] = sum_trials ( post_vsmGP[k] + m_k m_k^T ),   post_vsmGP[k] = eps diag(P_t[k,k]) + Y_k Y_k^T,
+// so in the EM loop the per-trial T x T blocks never have to reach HBM: S_k = sum_slots Y_k Y_k^T is ONE symmetric
+// product per latent with the reduction dimension (slot, c) of length slots * r.
+//
+// The lower block triangle of the T x T output (8 x 8 DMMA blocks) is cut into square tiles of tb = 8 blocks (64 x 64)
+// plus a remainder strip.  A CTA = one tile pair x one latent x one part of the slots; its 8 warps form a 4 x 2 grid
+// and every warp owns a FULL (tb/4) x (tb/2) rectangle of accumulator blocks, the same compile-time shape for the
+// whole launch.  That matters twice (both measured with ncu on the first versions of this kernel): a predicated-off
+// mma.sync still occupies the FP64 pipe for its 16 cycles (220 M DMMA issued for 128 M useful), and per-warp shapes
+// through a switch over template instances thrash the instruction cache (stall "no instruction" 6 per issue).  In a
+// diagonal tile the two warps whose rectangle lies above the diagonal only help with the loads.  The strip (T = 200:
+// one block row of 25) goes through a generic variant of the same kernel with run-time rectangle bounds.
+// Operands arrive through a 3-stage cp.async ring of 16-wide k-chunks that runs on across slot boundaries; one
+// 16-byte shared-memory load per lane feeds two k4-steps.  Parts are sized by the pairs' block counts so that all CTAs
+// carry the same work; every CTA writes its partial tile, a second kernel adds the parts in a fixed order
+// (deterministic) together with the eps diag(P) and m m^T terms.
+// ---------------------------------------------------------------------------------------------
+#define SY_MAXPAIRS 40
+#define SY_LD 24                                     // row pitch (doubles): 16-byte fragment loads of a quarter-warp hit 8 distinct 16-byte banks
+#ifndef SY_STAGES
+#define SY_STAGES 3
+#endif
+struct SyrkPair { int r0, nr, c0, nc, nparts, part0, diag; long long out_off; };
+struct SyrkArgs {
+    const double *Y;          // (slots, q*T, r)
+    double *partial;          // per latent: concatenated [pair][part][nr*nc]
+    long long strideY, partial_per_latent;
+    int r, T, q, nslots, npairs;
+    int first, count;         // pairs [first, first + count) belong to this launch
+    int dbg;                  // development switch (PGPFA_SYRK_DBG): 1 = loads only, 2 = MMAs only
+    SyrkPair pairs[SY_MAXPAIRS];
+};
+
+// 16-byte asynchronous copy global -> shared (both addresses 16-byte aligned); src_bytes in {0, 8, 16}, the rest is zero-filled
+__device__ __forceinline__ void cp_async16(double *dst_smem, const double *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+
+// every warp owns a full MI x NJ rectangle, CTA tile (4 MI) x (2 NJ) blocks (the pair's nr = 32 MI, nc = 16 NJ: full
+// tiles, no row checks anywhere).  V16: r is even, so every row of Y starts 16-byte aligned and the copies move two
+// columns at a time.
+template <int MI, int NJ, bool V16>
+__global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant__ SyrkArgs a) {
+    constexpr int ROWS = 32 * MI, COLS = 16 * NJ;
+    constexpr int STAGE = (ROWS + COLS) * SY_LD;
+    extern __shared__ __align__(16) double ssm[];
+    const int k = blockIdx.y;
+    int pidx = 0;
+    while (pidx + 1 < a.count && (int)blockIdx.x >= a.pairs[pidx + 1].part0) pidx++;
+    // everything the loops need from the argument block lives in registers (indexed reads of the parameter space are
+    // LDC instructions with a long scoreboard: they were the top stall of the first version)
+    const int r0 = a.pairs[pidx].r0, c0 = a.pairs[pidx].c0, diag = a.pairs[pidx].diag, nparts = a.pairs[pidx].nparts;
+    const int part = blockIdx.x - a.pairs[pidx].part0;
+    const long long out_off = a.pairs[pidx].out_off;
+    const int r = a.r;
+    const long long strideY = a.strideY;
+    const int s_begin = (int)((long long)a.nslots * part / nparts), s_end = (int)((long long)a.nslots * (part + 1) / nparts);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    // warp rectangle: 4 row groups x 2 column halves (a warp lives on SM sub-partition warp % 4 with its own FP64 pipe)
+    // In a diagonal tile two of the eight rectangles are not needed; which pipes they idle rotates with the CTA index
+    // so that co-resident CTAs do not starve the same pipes.
+    const int wn = warp >> 2, g = ((warp & 3) + (diag ? (int)blockIdx.x : 0)) & 3;
+    const int base_m = g * MI, base_n = wn * NJ;
+    // a rectangle entirely above the diagonal of a diagonal tile is not needed (its warp only helps with the loads)
+    const bool active = !diag || base_m + MI - 1 >= base_n;
+    const int nchunks = (r + 15) >> 4;
+    const int total = (s_end - s_begin) * nchunks;
+    // loader.  V16: thread (lr = tid / 8, lc2 = tid % 8) copies columns 2 lc2, 2 lc2 + 1 of rows lr + 32 u;
+    // else: thread (lr = tid / 16, lc = tid % 16) copies column lc of rows lr + 16 u.
+    const int lr = V16 ? tid >> 3 : tid >> 4, lc = V16 ? 2 * (tid & 7) : tid & 15;
+    constexpr int RSTEP = V16 ? 32 : 16;
+    const double *pa = a.Y + (size_t)s_begin * strideY + ((size_t)k * a.T + r0 + lr) * r + lc;
+    const double *pb = a.Y + (size_t)s_begin * strideY + ((size_t)k * a.T + c0 + lr) * r + lc;
+    const size_t rstep = (size_t)RSTEP * r;
+    int ld_chunk = 0;
+    auto stage_load = [&](int st) {
+        double *As = ssm + (size_t)st * STAGE + lr * SY_LD + lc, *Bs = As + ROWS * SY_LD;
+        const int left = r - (ld_chunk * 16 + lc);                 // columns left from this thread's first one
+        const int nb = V16 ? (left >= 2 ? 16 : (left == 1 ? 8 : 0)) : (left >= 1 ? 8 : 0);
+        const double *sa = nb ? pa : a.Y, *sb = nb ? pb : a.Y;
+#pragma unroll
+        for (int u = 0; u < ROWS / RSTEP; u++) {
+            if (V16) cp_async16(As + u * RSTEP * SY_LD, sa + (nb ? u * rstep : 0), nb);
+            else cp_async8(As + u * RSTEP * SY_LD, sa + (nb ? u * rstep : 0), nb);
+        }
+        if (!diag) {
+#pragma unroll
+            for (int u = 0; u < COLS / RSTEP; u++) {
+                if (V16) cp_async16(Bs + u * RSTEP * SY_LD, sb + (nb ? u * rstep : 0), nb);
+                else cp_async8(Bs + u * RSTEP * SY_LD, sb + (nb ? u * rstep : 0), nb);
+            }
+        }
+        pa += 16; pb += 16;
+        if (++ld_chunk == nchunks) { ld_chunk = 0; pa += strideY - (size_t)nchunks * 16; pb += strideY - (size_t)nchunks * 16; }
+    };
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll
+    for (int s0 = 0; s0 < SY_STAGES - 1; s0++) {
+        if (s0 < total) stage_load(s0);
+        cp_async_commit();
+    }
+    int st_cur = 0, st_load = SY_STAGES - 1;
+    for (int it = 0; it < total; it++) {
+        cp_async_wait<SY_STAGES - 2>();
+        __syncthreads();
+        if (it + SY_STAGES - 1 < total && a.dbg != 2) stage_load(st_load);
+        cp_async_commit();
+        if (active && a.dbg != 1) {
+            const double *As = ssm + (size_t)st_cur * STAGE;
+            const double *Bs = diag ? As : As + ROWS * SY_LD;
+            // one 16-byte load per lane and block feeds TWO k4-steps: lane (fr, fk) takes columns 2fk, 2fk+1 of an 8-wide
+            // k-group, .x goes into the first MMA and .y into the second.  Both operands use the same permutation of k
+            // inside the group, which a dot product does not see.
+#pragma unroll
+            for (int k8 = 0; k8 < 16; k8 += 8) {
+                double2 av[MI], bv[NJ];
+#pragma unroll
+                for (int i = 0; i < MI; i++)
+                    av[i] = *reinterpret_cast<const double2 *>(As + ((base_m + i) * 8 + fr) * SY_LD + k8 + 2 * fk);
+#pragma unroll
+                for (int j = 0; j < NJ; j++)
+                    bv[j] = *reinterpret_cast<const double2 *>(Bs + ((base_n + j) * 8 + fr) * SY_LD + k8 + 2 * fk);
+#pragma unroll
+                for (int i = 0; i < MI; i++)
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].x, bv[j].x);
+#pragma unroll
+                for (int i = 0; i < MI; i++)
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i].y, bv[j].y);
+            }
+        }
+        st_cur = (st_cur + 1 == SY_STAGES) ? 0 : st_cur + 1;
+        st_load = (st_load + 1 == SY_STAGES) ? 0 : st_load + 1;
+    }
+    if (!active) return;
+    double *out = a.partial + (size_t)k * a.partial_per_latent + out_off + (size_t)part * ROWS * COLS;
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            // (blocks above the diagonal inside a kept rectangle hold correct values too; the finishing kernel only reads
+            // the lower triangle)
+            const int row = (base_m + i) * 8 + fr, col = (base_n + j) * 8 + 2 * fk;
+            *reinterpret_cast<double2 *>(out + (size_t)row * COLS + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+}
+
+// Remainder strip of the PautoSum product (rows [s0, T) that no full tile covers; T = 200: one 8-row block against all
+// 25 column blocks).  Too thin for the tile kernel (a CTA-wide barrier per 16-wide chunk for a handful of MMAs), so
+// the reduction dimension is split over WARPS instead: every warp owns a subset of the slots and keeps the
+// accumulators of one strip block row against a group of SYS_NB column blocks; its MMAs are fed straight from L2 (one
+// 8-byte load per lane and fragment — the rows were just streamed by the tile kernel), the fragments of the next k4-step
+// are in flight while the current one is multiplied.  No shared memory, no barriers; each warp writes its own partial
+// strip, the finishing kernel adds them in order.
+#define SYS_NB 13
+__global__ void __launch_bounds__(256, 2) syrk_strip_kernel(const __grid_constant__ SyrkArgs a, int pair_index, int warps_total,
+                                                            int ngroups) {
+    const int r0 = a.pairs[pair_index].r0, nr = a.pairs[pair_index].nr, nc = a.pairs[pair_index].nc;
+    const long long out_off = a.pairs[pair_index].out_off;
+    const int k = blockIdx.y, sbrow = blockIdx.z / ngroups, grp = blockIdx.z - sbrow * ngroups;
+    const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5);      // global warp = part
+    const int fr = lane >> 2, fk = lane & 3;
+    const int row0 = r0 + sbrow * 8;                              // first row of this strip block row
+    const int nbc = (row0 >> 3) + 1;                              // column blocks 0 .. own diagonal block are needed
+    const int jb = grp * SYS_NB;                                  // first column block of this group
+    const int nb = max(0, min(SYS_NB, nbc - jb));
+    if (nb == 0) return;
+    const int T = a.T, r = a.r;
+    const int s_begin = (int)((long long)a.nslots * gw / warps_total), s_end = (int)((long long)a.nslots * (gw + 1) / warps_total);
+    double acc[SYS_NB][2];
+#pragma unroll
+    for (int j = 0; j < SYS_NB; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    const bool aok = row0 + fr < T;
+    const int aoff = min(row0 + fr, T - 1) * r;               // T r < 2^31 (T <= 640)
+    int boff[SYS_NB];
+    unsigned bok = 0;
+#pragma unroll
+    for (int j = 0; j < SYS_NB; j++) {
+        const int brow = (jb + j) * 8 + fr;
+        if (j < nb && brow < T) bok |= 1u << j;
+        boff[j] = min(brow, T - 1) * r;
+    }
+    const int nk4 = (r + 3) >> 2;
+    for (int slot = s_begin; slot < s_end; slot++) {
+        const double *Yk = a.Y + (size_t)slot * a.strideY + (size_t)k * T * r;
+        double av, bv[SYS_NB];
+        auto fetch = [&](int k4, double &fa, double *fb) {
+            const int c = k4 * 4 + fk;
+            const bool cok = c < r;
+            const double *col = Yk + (cok ? c : 0);
+            fa = (aok && cok) ? col[aoff] : 0.0;
+#pragma unroll
+            for (int j = 0; j < SYS_NB; j++) fb[j] = (cok && ((bok >> j) & 1)) ? col[boff[j]] : 0.0;
+        };
+        fetch(0, av, bv);
+        for (int k4 = 0; k4 < nk4; k4++) {
+            double an = 0.0, bn[SYS_NB];
+            if (k4 + 1 < nk4) fetch(k4 + 1, an, bn);
+#pragma unroll
+            for (int j = 0; j < SYS_NB; j++) dmma884(acc[j][0], acc[j][1], av, bv[j]);       // full frame: no predicated-off MMA
+            av = an;
+#pragma unroll
+            for (int j = 0; j < SYS_NB; j++) bv[j] = bn[j];
+        }
+    }
+    // partial strip of this warp: [part = gw][nr rows][nc = T cols] inside the pair's area
+    double *out = a.partial + (size_t)k * a.partial_per_latent + out_off + (size_t)gw * nr * nc;
+#pragma unroll
+    for (int j = 0; j < SYS_NB; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int row = sbrow * 8 + fr, col = (jb + j) * 8 + 2 * fk + e;
+            if (j < nb && row < nr && col < nc) out[(size_t)row * nc + col] = acc[j][e];
+        }
+}
+
+// PautoSum[k][s][t] (+)= sum_parts partial + [s == t] eps sum_slots P_t[k,k] + sum_slots m[trial,k,s] m[trial,k,t]
+__global__ void __launch_bounds__(256) syrk_finish_kernel(const __grid_constant__ SyrkArgs a, const double *__restrict__ Pm, const double *__restrict__ m,
+                                                          const int *__restrict__ act, double eps, int accumulate,
+                                                          double *__restrict__ Pout) {
+    const int k = blockIdx.y, T = a.T, q = a.q;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int s = e / T, t = e - s * T;
+    const int rs = max(s, t), ct = min(s, t);
+    double v = 0.0;
+    for (int p = 0; p < a.npairs; p++) {
+        const SyrkPair pr = a.pairs[p];
+        if (rs < pr.r0 || rs >= pr.r0 + pr.nr || ct < pr.c0 || ct >= pr.c0 + pr.nc) continue;
+        const double *src = a.partial + (size_t)k * a.partial_per_latent + pr.out_off + (size_t)(rs - pr.r0) * pr.nc + (ct - pr.c0);
+        for (int j = 0; j < pr.nparts; j++) v += src[(size_t)j * pr.nr * pr.nc];
+        break;
+    }
+    double d0 = 0.0, d1 = 0.0;
+    const size_t strideM = (size_t)q * T;
+    const double *mp = m + (size_t)k * T;
+    int sl = 0;
+    for (; sl + 1 < a.nslots; sl += 2) {
+        const int r0 = act ? act[sl] : sl, r1 = act ? act[sl + 1] : sl + 1;
+        d0 += mp[(size_t)r0 * strideM + s] * mp[(size_t)r0 * strideM + t];
+        d1 += mp[(size_t)r1 * strideM + s] * mp[(size_t)r1 * strideM + t];
+    }
+    if (sl < a.nslots) { const int r0 = act ? act[sl] : sl; d0 += mp[(size_t)r0 * strideM + s] * mp[(size_t)r0 * strideM + t]; }
+    v += d0 + d1;
+    if (s == t) {
+        double pd = 0.0;
+        for (int sl2 = 0; sl2 < a.nslots; sl2++) pd += Pm[((size_t)sl2 * q * q + k * q + k) * T + t];
+        v += eps * pd;
+    }
+    double *o = Pout + (size_t)k * T * T + e;
+    *o = (accumulate ? *o : 0.0) + v;
+}
+
 // Zd[slot][c][a] = (L_b^-1)[c][a] from the packed-upper tiles ZT = L_b^-T (row-major r x r, lower triangular)
 __global__ void zt_to_dense_lower_kernel(const double *__restrict__ ZT, int nb, int r, double *__restrict__ Zd) {
     const int slot = blockIdx.y;
@@ -541,6 +804,92 @@ LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
 }
 }  // namespace
 
+// Tile pairs and parts of the PautoSum product for a T x T output and `nslots` slots.  Pairs [0, n_uniform) are
+// full tb x tb tiles (uniform kernel), the rest covers the remainder strip (generic kernel).  Returns tb.
+static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int &grid_uniform, int &grid_generic) {
+    const int nblk = (T + 7) / 8;
+    int tb = 0;
+    // 8-block (64 x 64) tiles: with more, smaller tiles a smaller share of the issued MMAs falls into the half-empty
+    // diagonal tiles (T = 200: 384 issued blocks for 300 useful; 12-block tiles: 432), measured 6.5 vs 7.4 ms
+    tb = nblk >= 8 ? 8 : 0;
+    const int nt = tb ? nblk / tb : 0;
+    int weights[SY_MAXPAIRS];
+    a.npairs = 0;
+    long long wsum = 0;
+    auto add = [&](int r0, int nr, int c0, int nc, int diag, int w) {
+        SyrkPair &p = a.pairs[a.npairs];
+        p.r0 = r0; p.nr = nr; p.c0 = c0; p.nc = nc; p.diag = diag;
+        weights[a.npairs++] = w;
+        wsum += w;
+    };
+    for (int ti = 0; ti < nt; ti++)
+        for (int tj = 0; tj <= ti; tj++)
+            add(ti * tb * 8, tb * 8, tj * tb * 8, tb * 8, ti == tj, 1);     // equal weights: a diagonal CTA's busiest
+                                                                           // pipes carry a full tile's load per slot
+    n_uniform = a.npairs;
+    const int s0 = nt * tb * 8;                               // first row of the strip
+    const int budget = std::max(std::max(n_uniform, 1), (2 * 148) / std::max(q, 1));    // tile CTAs per latent: about two per SM over all latents
+    long long off = 0;
+    int part0 = 0;
+    for (int p = 0; p < n_uniform; p++) {
+        int np = (int)((weights[p] * (long long)budget + wsum / 2) / wsum);
+        np = std::max(1, std::min(np, nslots));
+        a.pairs[p].nparts = np;
+        a.pairs[p].part0 = part0;
+        a.pairs[p].out_off = off;
+        part0 += np;
+        off += (long long)np * a.pairs[p].nr * a.pairs[p].nc;
+    }
+    grid_uniform = part0;
+    grid_generic = 0;
+    if (s0 < T) {
+        // strip pair: rows [s0, T) against columns [0, T); one part per warp of the strip kernel (8 warps per CTA)
+        SyrkPair &p = a.pairs[a.npairs];
+        p.r0 = s0; p.nr = T - s0; p.c0 = 0; p.nc = T; p.diag = 0;
+        const int sbrows = (p.nr + 7) / 8;
+        const int ngroups = ((T + 7) / 8 + 12) / 13;                           // column groups of the strip kernel (SYS_NB)
+        int ctas = std::max(1, (2 * 148) / std::max(q * sbrows * ngroups, 1));  // strip CTAs per latent, block row and group
+        ctas = std::max(1, std::min(ctas, (nslots + 7) / 8));
+        p.nparts = ctas * 8;
+        p.part0 = 0;
+        p.out_off = off;
+        off += (long long)p.nparts * p.nr * p.nc;
+        grid_generic = ctas;
+        a.npairs++;
+    }
+    a.partial_per_latent = (off + 1) & ~1LL;                 // even: 16-byte stores into the areas of later latents
+    return tb;
+}
+
+size_t pgpfa_i_pautosum_partial_bytes(int q, int T) {
+    SyrkArgs a;
+    int nu, gu, gg;
+    syrk_plan(a, T, 1 << 20, q, nu, gu, gg);
+    return align_up((size_t)q * a.partial_per_latent * 8);
+}
+
+template <int MI, int NJ, bool V16>
+static int syrk_launch1(const SyrkArgs &a, int grid_x, int q, cudaStream_t st) {
+    constexpr int ROWS = 32 * MI, COLS = 16 * NJ;
+    constexpr int smem = SY_STAGES * (ROWS + COLS) * SY_LD * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(syrk_sum_kernel<MI, NJ, V16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid(grid_x, q);
+    syrk_sum_kernel<MI, NJ, V16><<<grid, 256, smem, st>>>(a);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+template <int MI, int NJ>
+static int syrk_launch(const SyrkArgs &a, int grid_x, int q, cudaStream_t st) {
+    if (grid_x <= 0) return PGPFA_OK;
+    // 16-byte copies need every row of Y 16-byte aligned: r even (the slot stride q T r is then even too) and an aligned base
+    const bool v16 = (a.r % 2 == 0) && (reinterpret_cast<size_t>(a.Y) % 16 == 0);
+    return v16 ? syrk_launch1<MI, NJ, true>(a, grid_x, q, st) : syrk_launch1<MI, NJ, false>(a, grid_x, q, st);
+}
+
 #define LR_DISPATCH(FN, ...)                                   \
     switch (q) {                                               \
         LR_CASES(FN, __VA_ARGS__)                              \
@@ -578,7 +927,8 @@ int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, in
 // time-diagonal blocks (event `ev_means` is recorded here: x / vsm final), then the T x T blocks of every latent.
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
-                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st, int *info) {
+                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st, int *info,
+                              double *pautosum, int pauto_accumulate, const double *post_mean, double *pauto_partial) {
     if (nslots <= 0) return PGPFA_OK;
     const int r = lr.r, n = q * T, nbr = pgpfa_nb(r);
     const long long ltr = pgpfa_ltiles(nbr);
@@ -658,6 +1008,30 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
         PGPFA_TRY(launch_gemm(g, dprobs + 2 * qq, (int)tb.blk.size(), tb.blk_tiles, nslots, st));
         pgpfa_prof_end(h, st);
         // algorithmic work of the q symmetric T x T x r products: T (T+1) r flops each
+        h->prof_work[PGPFA_PROF_SLICES] += (double)nslots * q * (double)T * (T + 1) * r;
+    }
+    if (pautosum) {
+        // the trial-sum of the same products without the per-trial blocks ever reaching HBM
+        if (T > 575 || !pauto_partial || !post_mean) return PGPFA_ERR_ARG;     // <= SY_MAXPAIRS tile pairs (8 x 9 / 2 + strip)
+        pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
+        SyrkArgs a;
+        a.Y = Y; a.partial = pauto_partial; a.strideY = (long long)n * r; a.r = r; a.T = T; a.q = q; a.nslots = nslots;
+        int n_uniform = 0, grid_uniform = 0, grid_generic = 0;
+        const int tb = syrk_plan(a, T, nslots, q, n_uniform, grid_uniform, grid_generic);
+        a.first = 0; a.count = n_uniform;          // the tile kernel reads pairs [0, count)
+        { const char *e = getenv("PGPFA_SYRK_DBG"); a.dbg = e ? atoi(e) : 0; }
+        if (tb == 8) PGPFA_TRY((syrk_launch<2, 4>(a, grid_uniform, q, st)));
+        if (grid_generic > 0) {
+            const SyrkPair &sp = a.pairs[a.npairs - 1];
+            const int ngroups = ((T + 7) / 8 + SYS_NB - 1) / SYS_NB;
+            dim3 gs(grid_generic, q, ((sp.nr + 7) / 8) * ngroups);
+            syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups);
+            PGPFA_LAUNCH_CHECK();
+        }
+        dim3 gfin((T * T + 255) / 256, q);
+        syrk_finish_kernel<<<gfin, 256, 0, st>>>(a, Pm, post_mean, act, lr.eps, pauto_accumulate, pautosum);
+        PGPFA_LAUNCH_CHECK();
+        pgpfa_prof_end(h, st);
         h->prof_work[PGPFA_PROF_SLICES] += (double)nslots * q * (double)T * (T + 1) * r;
     }
     return PGPFA_OK;

@@ -120,7 +120,9 @@ int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, in
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
                               double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st,
-                              int *info = nullptr);
+                              int *info = nullptr, double *pautosum = nullptr, int pauto_accumulate = 0,
+                              const double *post_mean = nullptr, double *pauto_partial = nullptr);
+size_t pgpfa_i_pautosum_partial_bytes(int q, int T);
 int pgpfa_i_iota(int *p, int n, int start, cudaStream_t st);
 int pgpfa_i_compact(const int *act_in, int n_in, const int *conv, int keep_mask, int *act_out, int *n_out, cudaStream_t st,
                     const int *n_in_dev = nullptr, int *prog = nullptr);

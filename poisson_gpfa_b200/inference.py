@@ -115,6 +115,22 @@ class _TrialView:
         return (self[i] for i in range(len(self)))
 
 
+class _LazyTrialView(_TrialView):
+    """Per-trial view over a device tensor that is only produced on first access (post_vsmGP)."""
+
+    def __init__(self, make, length, fn=None):
+        self._make, self._len, self._fn, self._t = make, length, fn, None
+
+    @property
+    def tensor(self):
+        if self._t is None:
+            self._t = self._make()
+        return self._t
+
+    def __len__(self):
+        return self._len
+
+
 class _CovView:
     """post_cov[r]: full qT x qT posterior covariance of trial r, built on demand on the device."""
 
@@ -151,7 +167,7 @@ class InfRes(dict):
         self['post_mean'] = _TrialView(est.x)
         self['post_cov'] = _CovView(est, diag_scale, W_fn)
         self['post_vsm'] = _TrialView(est.vsm)
-        self['post_vsmGP'] = _TrialView(est.vsmGP, lambda a: a.permute(1, 2, 0).contiguous())
+        self['post_vsmGP'] = _LazyTrialView(est.get_vsmGP, est.x.shape[0], lambda a: a.permute(1, 2, 0).contiguous())
 
 
 def as_estep_result(infRes, experiment, params=None):
@@ -232,7 +248,9 @@ def laplace(experiment, params, prevOptimRes=None, returnOptimRes=True, verbose=
             else:
                 x0 = _f64(np.stack([np.asarray(prevOptimRes[i], dtype=np.float64).reshape(p.q, T)
                                     for i in range(lo_, lo_ + trials.R)]))
-    est = trials.estep_laplace(p, x0=x0, tol=tol)
+    # the per-trial T x T blocks of post_vsmGP are produced on first access (infRes['post_vsmGP']); the M-step only needs
+    # their trial-sum, which the E-step delivers directly
+    est = trials.estep_laplace(p, x0=x0, tol=tol, want_vsmGP=False, want_pautosum=True)
     if verbose:
         print('laplace inference: %d trials, Newton iterations max %d, factorisations %d'
               % (trials.R, est.stats['max_newton_iters'], est.stats['factorizations']))

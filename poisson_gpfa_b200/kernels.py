@@ -175,7 +175,7 @@ def hessian_dense(Kinv, W, diag_scale=1.0):
 
 
 class LaplaceResult:
-    __slots__ = ("x", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc")
+    __slots__ = ("x", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc", "pautosum")
 
 
 def prior_lowrank_async(K, eps=0.001, delta=1e-14):
@@ -194,10 +194,12 @@ def prior_lowrank(K, eps=0.001, delta=1e-14):
 
 
 def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True, want_vsmGP=True, want_cov=False,
-                  max_ws_bytes=None, ws=None, inexact_newton=True, lowrank=None):
+                  max_ws_bytes=None, ws=None, inexact_newton=True, lowrank=None, want_pautosum=False):
     """Batched Newton E-step (pgpfa_laplace_solve). y (R,N,T); returns LaplaceResult with device tensors.
     lowrank = (F, Ft, ranks, eps) from prior_lowrank: posterior pass through the low-rank prior factor
-    (pgpfa_laplace_solve_lowrank; not with want_cov)."""
+    (pgpfa_laplace_solve_lowrank; not with want_cov).  want_pautosum (low-rank pass only): res.pautosum (q,T,T) = the
+    trial-sum of post_vsmGP + m m^T computed inside the pass; together with want_vsmGP=False the per-trial blocks are
+    never written."""
     R, N, T = y.shape
     q = C.shape[1]
     x = torch.zeros(R, q, T, dtype=torch.float64, device="cuda") if x0 is None else x0.clone()
@@ -206,6 +208,7 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
     res.f = empty(R)
     res.vsm = empty(R, T, q, q) if want_vsm else None
     res.vsmGP = empty(R, q, T, T) if want_vsmGP else None
+    res.pautosum = None
     res.cov = empty(R, q * T, q * T) if want_cov else None
     res.niter = empty(R, dtype=torch.int32)
     res.info = empty(R, dtype=torch.int32)
@@ -222,15 +225,22 @@ def laplace_solve(y, C, d, Kinv, x0=None, tol=1e-8, max_newton=50, want_vsm=True
     if lowrank is not None and not want_cov:
         F, Ft, ranks, eps = lowrank
         rank_host = (ctypes.c_int * q)(*[int(v) for v in ranks])
+        if want_pautosum:
+            res.pautosum = empty(q, T, T)
         res.rc = call("pgpfa_laplace_solve_lowrank", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(F), ptr(Ft),
                       ctypes.cast(rank_host, ctypes.c_void_p), float(eps), ptr(x), R, q, N, T, float(tol), int(max_newton),
-                      int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.niter), ptr(res.info),
+                      int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.pautosum), ptr(res.niter),
+                      ptr(res.info),
                       ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(), allow=(_lib.ERR_NOT_CONVERGED,))
     else:
+        if want_pautosum and res.vsmGP is None:          # dense tiled path: the sum is taken over the per-trial blocks
+            res.vsmGP = empty(R, q, T, T)
         res.rc = call("pgpfa_laplace_solve", handle(), ptr(y), ptr(C), ptr(d), ptr(Kinv), ptr(x), R, q, N, T, float(tol),
                       int(max_newton), int(bool(inexact_newton)), ptr(res.f), ptr(res.vsm), ptr(res.vsmGP), ptr(res.cov),
                       ptr(res.niter), ptr(res.info), ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), stream(),
                       allow=(_lib.ERR_NOT_CONVERGED,))
+        if want_pautosum:
+            res.pautosum = pautosum(res.vsmGP, res.x)
     res.stats = {"factorizations": stats[0], "max_newton_iters": stats[1], "not_converged": stats[2],
                  "chunk": stats[3], "pcg_newton_iters": stats[4], "fallback_trials": stats[5], "lowrank_r": stats[6],
                  "fresh_chord_sweeps": stats[7] % 1000, "pcg_iters": stats[7] // 1000}

@@ -199,6 +199,34 @@ def test_engine_online_hess_and_grad_rules(method):
         assert rel(fit.cumHess[-1], g['cumHess_last']) <= 5e-3
 
 
+def test_analytic_hessian_blocks_match_the_references_fd_jacobian():
+    """Function-level pin of the online 'hess' / 'grad' rules: the reference builds
+    invPriorCov = -J with J the 4th-order finite-difference Jacobian (funs/util.py:377-434, step from statsmodels'
+    _get_epsilon) of the prior-cost gradient at the old parameters (funs/learning.py:545-549), and the 'grad' rule's
+    Hessian the same way (:884-891).  Ours are the analytic per-neuron blocks from the statistics kernel.  Inputs are
+    the same up to the E-step of the first mini-batch (reference: scipy Newton-CG at tightened tolerance, ~1e-7 from
+    the mode); the FD Jacobian itself is accurate to ~1e-7 relative, so the bound is 1e-6 (measured ~3e-8)."""
+    from poisson_gpfa_b200 import engine
+    for method, key in (("hess", "invPriorCov_1"), ("grad", "cumHess_1")):
+        g = load_golden("example_online_%s" % method)
+        ex = Exp(g)
+        np.random.seed(int(g['seed']))
+        fit = engine.PPGPFAfit(experiment=ex, initParams=init_params(g), inferenceMethod='laplace', EMmode='Online',
+                               maxEMiter=1, batchSize=int(g['batchSize']), onlineParamUpdateMethod=method, quiet=True)
+        ours = fit.invPriorCovs[1] if method == "hess" else fit.cumHess[1]
+        ref = g[key]
+        N, q = g['init_C'].shape
+        P = q + 1
+        pos = (np.arange(P)[:, None] * N + np.arange(N)[None, :])          # vec index of theta[n,k] (funs/util.py:560-574)
+        mask = np.zeros_like(ref, dtype=bool)
+        for n in range(N):
+            mask[np.ix_(pos[:, n], pos[:, n])] = True
+        scale = np.abs(ref[mask]).max()
+        assert np.abs(ours[mask] - ref[mask]).max() <= 1e-6 * scale
+        # the exact Hessian is block diagonal over neurons: what the reference has off the blocks is its FD noise
+        assert np.abs(ref[~mask]).max() <= 1e-6 * scale and np.abs(ours[~mask]).max() == 0.0
+
+
 def test_online_minibatch_gathers_from_resident_parent_with_Y_all():
     """Regression: a mini-batch made by util.subsampleTrials must not inherit the parent's stacked counts."""
     from poisson_gpfa_b200 import engine, inference, util

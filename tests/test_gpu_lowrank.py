@@ -69,3 +69,44 @@ def test_short_timescales_fall_back_to_the_dense_path():
     assert p.lowrank is None            # K - eps I has full numerical rank: nothing to gain
     p2 = core.DeviceParams(np.zeros((4, 2)), np.zeros(4), np.array([0.2, 0.4]), 50, 10.0)
     assert p2.lowrank is not None and sum(p2.lowrank[2]) < 50
+
+
+@pytest.mark.parametrize("q,N,T,R", [(2, 20, 50, 5), (3, 7, 40, 1), (8, 100, 200, 9), (3, 10, 129, 3), (10, 30, 250, 4),
+                                       (3, 15, 60, 70), (1, 5, 30, 2), (12, 20, 64, 3)])
+def test_pautosum_inside_the_lowrank_pass(q, N, T, R):
+    """makePrecomp's PautoSum (funs/learning.py:162-165) taken inside the posterior pass as ONE symmetric product per
+    latent over all trials (syrk_sum_kernel) against the sum over the per-trial post_vsmGP blocks of the same pass, and
+    against the oracle's sum over dense inverses."""
+    from poisson_gpfa_b200 import kernels as kn
+    ex, ys, params = problem(57 + q, q, N, T, R)
+    C, d, tau = dev(params['C']), dev(params['d']), dev(params['tau'])
+    y = dev(np.stack(ys))
+    K = kn.make_K(tau, T, 10.0, 0.001)
+    Kinv, _, _ = kn.spd_inverse(K)
+    lr = kn.prior_lowrank(K, 0.001, 1e-14) + (0.001,)
+    both = kn.laplace_solve(y, C, d, Kinv, lowrank=lr, want_vsmGP=True, want_pautosum=True)
+    only = kn.laplace_solve(y, C, d, Kinv, lowrank=lr, want_vsmGP=False, want_pautosum=True)
+    assert only.vsmGP is None and both.stats["lowrank_r"] > 0
+    ref = kn.pautosum(both.vsmGP, both.x)
+    assert rel(both.pautosum, ref.cpu().numpy()) <= 1e-13
+    assert torch.equal(only.pautosum, both.pautosum) and torch.equal(only.x, both.x)
+    assert rel(both.pautosum, both.pautosum.transpose(1, 2).cpu().numpy()) == 0.0      # exactly symmetric
+    ir, _, _, _ = po.laplace_struct(ys, params, T, 10, want_cov=False)
+    P_o = np.stack([pp['PautoSum'] for pp in po.make_precomp(ir)])
+    assert rel(both.pautosum, P_o) <= 1e-9
+
+
+def test_pautosum_chunked_pass_accumulates():
+    from poisson_gpfa_b200 import kernels as kn, _lib
+    q, N, T, R = 3, 9, 48, 11
+    ex, ys, params = problem(3, q, N, T, R)
+    C, d, tau = dev(params['C']), dev(params['d']), dev(params['tau'])
+    y = dev(np.stack(ys))
+    K = kn.make_K(tau, T, 10.0, 0.001)
+    Kinv, _, _ = kn.spd_inverse(K)
+    lr = kn.prior_lowrank(K, 0.001, 1e-14) + (0.001,)
+    full = kn.laplace_solve(y, C, d, Kinv, lowrank=lr, want_vsmGP=False, want_pautosum=True)
+    small = _lib.lib.pgpfa_laplace_workspace_bytes(R, q, T, 4)
+    chunked = kn.laplace_solve(y, C, d, Kinv, lowrank=lr, want_vsmGP=False, want_pautosum=True, max_ws_bytes=small)
+    assert chunked.stats["chunk"] < R
+    assert rel(chunked.pautosum, full.pautosum.cpu().numpy()) <= 1e-13
