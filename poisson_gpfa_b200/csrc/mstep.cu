@@ -381,14 +381,14 @@ extern "C" long long pgpfa_mstep_cd_workspace_bytes(int q, int N) {
 static int cd_stats_impl(const double *y, const double *m, const double *vsm, const double *theta, int R, int q, int N,
                          int T, double *stats, void *workspace, long long ws_bytes, cudaStream_t st,
                          const int *skip_if_zero) {
-    if (!y || !m || !vsm || !theta || !stats || !workspace || R < 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0)
-        return PGPFA_ERR_ARG;
-    if (ws_bytes < pgpfa_mstep_cd_workspace_bytes(q, N)) return PGPFA_ERR_WORKSPACE;
+    if (!stats || R < 0 || q <= 0 || q > PGPFA_QMAX || N <= 0 || T <= 0) return PGPFA_ERR_ARG;
     const int len = pgpfa_mstep_cd_nstats(q) * N;
     if (R == 0) {                  // a rank without trials (mini-batch smaller than the world) contributes zeros
         PGPFA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)len * 8, st));
         return PGPFA_OK;
     }
+    if (!y || !m || !vsm || !theta || !workspace) return PGPFA_ERR_ARG;
+    if (ws_bytes < pgpfa_mstep_cd_workspace_bytes(q, N)) return PGPFA_ERR_WORKSPACE;
     double *partial = reinterpret_cast<double *>(align_up(reinterpret_cast<size_t>(workspace)));
     const long long items = (long long)R * ((T + CD_TT - 1) / CD_TT);
     int nblocks = cd_blocks();
