@@ -267,6 +267,7 @@ class DeviceTrials:
         self._lap_ws = None
         self._cd_ws = None
         self._tau_ws = None
+        self._tau_blind = 3       # evaluation rounds of the timescale search enqueued blind: what the last search needed
 
     def _means_stream(self):
         """High-priority stream ordered after the point of the last Laplace solve where the posterior means and
@@ -500,7 +501,7 @@ class DeviceTrials:
             est = self.estep_variational(params, lam0=lam0)
         cd = self.mstep_cd_async(params, est, tol=cd_tol)
         Psum = self.pautosum(est)
-        ts = self.mstep_tau_async(params, Psum, xtol=tau_xtol)
+        ts = self.mstep_tau_async(params, Psum, xtol=tau_xtol, n_blind=self._tau_blind)
         cd.join()
         q = params.q
         newp = DeviceParams(cd.th_cur[:, :q].contiguous(), cd.th_cur[:, q].contiguous(), ts.tau, self.T, self.binSize)
@@ -513,6 +514,7 @@ class DeviceTrials:
         redo = v_cd[0][0] > 0 or v_ts[0][0] > 0
         C, d, cost, cd_it, _ = cd.finish(v_cd)
         tau = ts.finish(v_ts)
+        self._tau_blind = max(2, min(4, int(ts.flags_host[1])))       # steady-state EM: two rounds
         if redo:                      # a blind schedule was too short (rare): the prior was built from unfinished values
             newp = DeviceParams(C, d, tau, self.T, self.binSize)
         else:
