@@ -129,24 +129,38 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
         const int skip = loo.excl ? loo.excl[trial] : -1;
         const double *yp = y + (size_t)yrow * N * T + t;
         const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
-        for (int n = 0; n < N; n++) {
-            if (n == skip) continue;
-            double h = ds[n];
+        // neurons in groups of four: the four counts (and log-rate offsets) are in flight together, the row of C of a
+        // neuron is read once from shared memory into registers (every thread reads the same address: broadcast)
+        for (int n0 = 0; n0 < N; n0 += 4) {
+            double yv[4], ov[4];
 #pragma unroll
-            for (int k = 0; k < Q; k++) h += Cs[n * Q + k] * xk[k];
-            // variational path: rates carry the extra log-offset s[n,t] = 0.5 c_n^T Sigma_tt c_n
-            const double lam = op ? exp(h + op[(size_t)n * T]) : exp(h);
-            const double yy = yp[(size_t)n * T];
-            fl += lam - yy * h;
-            const double r = lam - yy;
-            int idx = 0;
+            for (int u = 0; u < 4; u++) {
+                const int n = n0 + u;
+                yv[u] = (n < N) ? yp[(size_t)n * T] : 0.0;
+                ov[u] = (op && n < N) ? op[(size_t)n * T] : 0.0;
+            }
 #pragma unroll
-            for (int k = 0; k < Q; k++) {
-                const double ck = Cs[n * Q + k];
-                gk[k] += ck * r;
-                const double cl = ck * lam;
+            for (int u = 0; u < 4; u++) {
+                const int n = n0 + u;
+                if (n >= N || n == skip) continue;
+                double c[Q];
 #pragma unroll
-                for (int l = k; l < Q; l++) { w[idx] += cl * Cs[n * Q + l]; idx++; }
+                for (int k = 0; k < Q; k++) c[k] = Cs[n * Q + k];
+                double h = ds[n];
+#pragma unroll
+                for (int k = 0; k < Q; k++) h = fma(c[k], xk[k], h);
+                // variational path: rates carry the extra log-offset s[n,t] = 0.5 c_n^T Sigma_tt c_n
+                const double lam = exp(h + ov[u]);
+                fl += fma(-yv[u], h, lam);
+                const double r = lam - yv[u];
+                int idx = 0;
+#pragma unroll
+                for (int k = 0; k < Q; k++) {
+                    gk[k] = fma(c[k], r, gk[k]);
+                    const double cl = c[k] * lam;
+#pragma unroll
+                    for (int l = k; l < Q; l++) { w[idx] = fma(cl, c[l], w[idx]); idx++; }
+                }
             }
         }
         int idx = 0;
@@ -212,13 +226,26 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
             const int skip = loo.excl ? loo.excl[trial] : -1;
             const double *yp = y + (size_t)yrow * N * T + t;
             const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
-            for (int n = 0; n < N; n++) {
-                if (n == skip) continue;
-                double h = ds[n], dh = 0.0;
+            double xa[Q];                                  // the trial point x + alpha dx of this bin
 #pragma unroll
-                for (int k = 0; k < Q; k++) { h += Cs[n * Q + k] * xk[k]; dh += Cs[n * Q + k] * dk[k]; }
-                const double ha = h + alpha * dh;
-                fl += (op ? exp(ha + op[(size_t)n * T]) : exp(ha)) - yp[(size_t)n * T] * ha;
+            for (int k = 0; k < Q; k++) xa[k] = fma(alpha, dk[k], xk[k]);
+            for (int n0 = 0; n0 < N; n0 += 4) {            // four neurons' counts in flight (see laplace_eval_kernel)
+                double yv[4], ov[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int n = n0 + u;
+                    yv[u] = (n < N) ? yp[(size_t)n * T] : 0.0;
+                    ov[u] = (op && n < N) ? op[(size_t)n * T] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int n = n0 + u;
+                    if (n >= N || n == skip) continue;
+                    double ha = ds[n];
+#pragma unroll
+                    for (int k = 0; k < Q; k++) ha = fma(Cs[n * Q + k], xa[k], ha);
+                    fl += fma(-yv[u], ha, exp(ha + ov[u]));
+                }
             }
         }
         fl = block_sum(fl, red);

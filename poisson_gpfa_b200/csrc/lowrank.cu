@@ -524,39 +524,53 @@ __global__ void __launch_bounds__(256, 2) syrk_strip_kernel(const __grid_constan
 }
 
 // PautoSum[k][s][t] (+)= sum_parts partial + [s == t] eps sum_slots P_t[k,k] + sum_slots m[trial,k,s] m[trial,k,t]
+// CTA = 16 x 16 output tile of one latent; the posterior means of 32 slots at a time go through shared memory (each
+// value is then used 16 times), all sums in a fixed order.
 __global__ void __launch_bounds__(256) syrk_finish_kernel(const __grid_constant__ SyrkArgs a, const double *__restrict__ Pm, const double *__restrict__ m,
                                                           const int *__restrict__ act, double eps, int accumulate,
                                                           double *__restrict__ Pout) {
-    const int k = blockIdx.y, T = a.T, q = a.q;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= T * T) return;
-    const int s = e / T, t = e - s * T;
-    const int rs = max(s, t), ct = min(s, t);
+    __shared__ double ms[32][17], mt[32][17];
+    const int k = blockIdx.z, T = a.T, q = a.q;
+    const int ts = threadIdx.x >> 4, tt = threadIdx.x & 15;
+    const int s = blockIdx.y * 16 + ts, t = blockIdx.x * 16 + tt;
+    const bool in = s < T && t < T;
     double v = 0.0;
-    for (int p = 0; p < a.npairs; p++) {
-        const SyrkPair pr = a.pairs[p];
-        if (rs < pr.r0 || rs >= pr.r0 + pr.nr || ct < pr.c0 || ct >= pr.c0 + pr.nc) continue;
-        const double *src = a.partial + (size_t)k * a.partial_per_latent + pr.out_off + (size_t)(rs - pr.r0) * pr.nc + (ct - pr.c0);
-        for (int j = 0; j < pr.nparts; j++) v += src[(size_t)j * pr.nr * pr.nc];
-        break;
+    if (in) {
+        const int rs = max(s, t), ct = min(s, t);
+        for (int p = 0; p < a.npairs; p++) {
+            const int r0 = a.pairs[p].r0, nr = a.pairs[p].nr, c0 = a.pairs[p].c0, nc = a.pairs[p].nc;
+            if (rs < r0 || rs >= r0 + nr || ct < c0 || ct >= c0 + nc) continue;
+            const double *src = a.partial + (size_t)k * a.partial_per_latent + a.pairs[p].out_off + (size_t)(rs - r0) * nc + (ct - c0);
+            const int np = a.pairs[p].nparts;
+            for (int j = 0; j < np; j++) v += src[(size_t)j * nr * nc];
+            break;
+        }
     }
-    double d0 = 0.0, d1 = 0.0;
     const size_t strideM = (size_t)q * T;
     const double *mp = m + (size_t)k * T;
-    int sl = 0;
-    for (; sl + 1 < a.nslots; sl += 2) {
-        const int r0 = act ? act[sl] : sl, r1 = act ? act[sl + 1] : sl + 1;
-        d0 += mp[(size_t)r0 * strideM + s] * mp[(size_t)r0 * strideM + t];
-        d1 += mp[(size_t)r1 * strideM + s] * mp[(size_t)r1 * strideM + t];
+    double d0 = 0.0;
+    for (int sl0 = 0; sl0 < a.nslots; sl0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * 32 * 16; i += 256) {
+            const int which = i >> 9, sl = (i >> 4) & 31, c = i & 15;
+            const int slot = sl0 + sl;
+            const int idx = (which ? blockIdx.x : blockIdx.y) * 16 + c;
+            double val = 0.0;
+            if (slot < a.nslots && idx < T) val = mp[(size_t)(act ? act[slot] : slot) * strideM + idx];
+            (which ? mt : ms)[sl][c] = val;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int sl = 0; sl < 32; sl++) d0 = fma(ms[sl][ts], mt[sl][tt], d0);
     }
-    if (sl < a.nslots) { const int r0 = act ? act[sl] : sl; d0 += mp[(size_t)r0 * strideM + s] * mp[(size_t)r0 * strideM + t]; }
-    v += d0 + d1;
+    if (!in) return;
+    v += d0;
     if (s == t) {
         double pd = 0.0;
         for (int sl2 = 0; sl2 < a.nslots; sl2++) pd += Pm[((size_t)sl2 * q * q + k * q + k) * T + t];
         v += eps * pd;
     }
-    double *o = Pout + (size_t)k * T * T + e;
+    double *o = Pout + (size_t)k * T * T + (size_t)s * T + t;
     *o = (accumulate ? *o : 0.0) + v;
 }
 
@@ -1028,7 +1042,7 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
             syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups);
             PGPFA_LAUNCH_CHECK();
         }
-        dim3 gfin((T * T + 255) / 256, q);
+        dim3 gfin((T + 15) / 16, (T + 15) / 16, q);
         syrk_finish_kernel<<<gfin, 256, 0, st>>>(a, Pm, post_mean, act, lr.eps, pauto_accumulate, pautosum);
         PGPFA_LAUNCH_CHECK();
         pgpfa_prof_end(h, st);
