@@ -90,7 +90,26 @@ def device_trials(experiment, reducer=None):
     return dt
 
 
+# Device-side parameter sets whose prior (K, K^-1, low-rank factor) is already built, keyed by the parameter VALUES:
+# learning.updateParams leaves the set it returns here, so the next inference.laplace(experiment, thoseParams) finds the
+# prior of its E-step ready (built on the device underneath the M-step's host read) instead of rebuilding it.
+_prepared = {}
+
+
+def _params_key(C, d, tau, T, binSize):
+    h = lambda a: hash(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes())
+    return (int(T), float(binSize), np.shape(C), h(C), h(d), h(tau))
+
+
+def remember_params(params_host, dparams):
+    _prepared.clear()              # one entry: the parameters of the iteration in flight
+    _prepared[_params_key(params_host['C'], params_host['d'], params_host['tau'], dparams.T, dparams.binSize)] = dparams
+
+
 def device_params(params, T, binSize):
+    hit = _prepared.get(_params_key(params['C'], params['d'], params['tau'], T, binSize)) if _prepared else None
+    if hit is not None:
+        return hit
     return DeviceParams(params['C'], params['d'], params['tau'], T, binSize)
 
 

@@ -213,10 +213,50 @@ def learnGPparamsWithPrior(oldParams, infRes, experiment, tauOptimMethod, regula
 
 # ---------------------------------------------------------------------------------------------- glue
 def updateParams(oldParams, infRes, experiment, CdOptimMethod='BFGS', CdMaxIter=None, tauMaxIter=None, verbose=False):
-    """(newParams, {'Cd': cost, 'tau': [details]}) — funs/learning.py:295-309."""
-    newC, newd, cost = learnLTparams(oldParams, infRes, experiment, CdOptimMethod, CdMaxIter, verbose)
-    newTau, det = learnGPparams(oldParams, infRes, experiment)
-    return {'C': newC, 'd': newd, 'tau': newTau}, {'Cd': cost, 'tau': det}
+    """(newParams, {'Cd': cost, 'tau': [details]}) — funs/learning.py:295-309.
+
+    learnLTparams and learnGPparams are enqueued together (the C,d Newton iterations on the stream where the posterior
+    means were final first, the timescale search behind the covariance sums), the prior of the NEXT E-step is built on
+    the device from the new parameters, and ONE packed read brings back the new parameters, the costs and every flag."""
+    from .core import read_packed
+    from .inference import remember_params
+    est = as_estep_result(infRes, experiment)
+    trials = est.trials
+    p = device_params(oldParams, trials.T, experiment.binSize)
+    q = p.q
+    cd = trials.mstep_cd_async(p, est, n_blind=min(4, CdMaxIter or 4))
+    Psum = trials.pautosum(est)
+    ts = trials.mstep_tau_async(p, Psum, n_blind=trials._tau_blind)
+    cd.join()
+    newp = DeviceParams(cd.th_cur[:, :q].contiguous(), cd.th_cur[:, q].contiguous(), ts.tau, trials.T, experiment.binSize)
+    pend_cd, pend_ts, pend_p = cd.pending(), ts.pending(), newp.pending()
+    cd.join()
+    vals = read_packed(pend_cd + pend_ts + pend_p + [newp.C, newp.d, newp.tau, ts.det])
+    v_cd, v_ts, v_p = vals[:3], vals[3:4], vals[4:4 + len(pend_p)]
+    Ch, dh, tauh, deth = vals[4 + len(pend_p):]
+    redo = v_cd[0][0] > 0 or v_ts[0][0] > 0
+    C, d, cost, it, _ = cd.finish(v_cd, max_iter=CdMaxIter or 100)
+    tau = ts.finish(v_ts)
+    trials._tau_blind = max(2, min(4, int(ts.flags_host[1])))
+    if not est._checked:
+        from .core import EStepResult
+        EStepResult.raise_on(cd.extra_host)
+        est._checked = True
+    if redo:          # a blind schedule was too short (rare): finish on the host's say-so and read the final values
+        Ch, dh, tauh, deth = read_packed([C, d, tau, ts.det])
+        newp = DeviceParams(C, d, tau, trials.T, experiment.binSize)
+    else:
+        newp.resolve(v_p)
+    new = {'C': Ch, 'd': dh, 'tau': tauh}
+    remember_params(new, newp)
+    fl = ts.flags_host
+    det = {'p': deth[0], 'p0': deth[1], 'grad': deth[2], 'fun': deth[3], 'nfev': int(fl[1]),
+           'bracketed': np.array([(int(fl[2]) >> k) & 1 for k in range(q)], dtype=bool)}
+    details = [OptimizeDetail(x=np.array([det['p'][k]]), fun=det['fun'][k], jac=np.array([det['grad'][k]]),
+                              nfev=det['nfev'], success=bool(det['bracketed'][k])) for k in range(q)]
+    if verbose:
+        print('Cd optimization: %d Newton iterations, cost %.10g; tau search: %d evaluations' % (it, cost, det['nfev']))
+    return new, {'Cd': cost, 'tau': details}
 
 
 def updateParamsWithPrior(oldParams, infRes, experiment, CdOptimMethod, tauOptimMethod, regularizer_stepsize_Cd,
