@@ -330,6 +330,7 @@ struct SyrkArgs {
     int r, T, q, nslots, npairs;
     int first, count;         // pairs [first, first + count) belong to this launch
     int dbg;                  // development switch (PGPFA_SYRK_DBG): 1 = loads only, 2 = MMAs only
+    int strip_pair, strip_r0, strip_nr;   // strip of <= 16 rows fused into the diagonal tiles' CTAs (strip_nr = 0: none)
     SyrkPair pairs[SY_MAXPAIRS];
 };
 
@@ -344,8 +345,8 @@ __device__ __forceinline__ void cp_async16(double *dst_smem, const double *src, 
 // columns at a time.
 template <int MI, int NJ, bool V16>
 __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant__ SyrkArgs a) {
-    constexpr int ROWS = 32 * MI, COLS = 16 * NJ;
-    constexpr int STAGE = (ROWS + COLS) * SY_LD;
+    constexpr int ROWS = 32 * MI, COLS = 16 * NJ, SROWS = 8 * MI;       // tile operands + the fused strip rows
+    constexpr int STAGE = (ROWS + COLS + SROWS) * SY_LD;
     extern __shared__ __align__(16) double ssm[];
     const int k = blockIdx.y;
     int pidx = 0;
@@ -364,9 +365,16 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
     // In a diagonal tile two of the eight rectangles are not needed; which pipes they idle rotates with the CTA index
     // so that co-resident CTAs do not starve the same pipes.
     const int wn = warp >> 2, g = ((warp & 3) + (diag ? (int)blockIdx.x : 0)) & 3;
-    const int base_m = g * MI, base_n = wn * NJ;
-    // a rectangle entirely above the diagonal of a diagonal tile is not needed (its warp only helps with the loads)
-    const bool active = !diag || base_m + MI - 1 >= base_n;
+    int base_m = g * MI, base_n = wn * NJ;
+    // A rectangle entirely above the diagonal of a diagonal tile is not needed.  When the remainder strip of the output
+    // (<= 8 MI rows below the last full tile) is fused in, these warps multiply the strip rows — staged behind the
+    // tile operands — with this tile's rows instead: strip x tile j comes out of diagonal CTA (j, j) for free.
+    const bool above = diag && base_m + MI - 1 < base_n;
+    const bool fuse_strip = diag && a.strip_nr > 0;
+    const bool strip_warp = above && fuse_strip;
+    const bool active = !above || strip_warp;
+    int aoff = 0, boff = diag ? 0 : ROWS * SY_LD;                 // operand regions inside a stage (doubles)
+    if (strip_warp) { aoff = (ROWS + COLS) * SY_LD; base_n = g * NJ; base_m = 0; }       // g in {0, 1}: the two column halves
     const int nchunks = (r + 15) >> 4;
     const int total = (s_end - s_begin) * nchunks;
     // loader.  V16: thread (lr = tid / 8, lc2 = tid % 8) copies columns 2 lc2, 2 lc2 + 1 of rows lr + 32 u;
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
     constexpr int RSTEP = V16 ? 32 : 16;
     const double *pa = a.Y + (size_t)s_begin * strideY + ((size_t)k * a.T + r0 + lr) * r + lc;
     const double *pb = a.Y + (size_t)s_begin * strideY + ((size_t)k * a.T + c0 + lr) * r + lc;
+    const double *ps = a.Y + (size_t)s_begin * strideY + ((size_t)k * a.T + min(a.strip_r0 + lr, a.T - 1)) * r + lc;
     const size_t rstep = (size_t)RSTEP * r;
     int ld_chunk = 0;
     auto stage_load = [&](int st) {
@@ -393,9 +402,17 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
                 if (V16) cp_async16(Bs + u * RSTEP * SY_LD, sb + (nb ? u * rstep : 0), nb);
                 else cp_async8(Bs + u * RSTEP * SY_LD, sb + (nb ? u * rstep : 0), nb);
             }
+        } else if (fuse_strip && lr < SROWS) {             // strip rows (zero-filled beyond strip_nr)
+            const int nbs = lr < a.strip_nr ? nb : 0;
+            double *Ss = ssm + (size_t)st * STAGE + (ROWS + COLS + lr) * SY_LD + lc;
+            if (V16) cp_async16(Ss, nbs ? ps : a.Y, nbs);
+            else cp_async8(Ss, nbs ? ps : a.Y, nbs);
         }
-        pa += 16; pb += 16;
-        if (++ld_chunk == nchunks) { ld_chunk = 0; pa += strideY - (size_t)nchunks * 16; pb += strideY - (size_t)nchunks * 16; }
+        pa += 16; pb += 16; ps += 16;
+        if (++ld_chunk == nchunks) {
+            ld_chunk = 0;
+            pa += strideY - (size_t)nchunks * 16; pb += strideY - (size_t)nchunks * 16; ps += strideY - (size_t)nchunks * 16;
+        }
     };
     double acc[MI][NJ][2];
 #pragma unroll
@@ -414,8 +431,8 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
         if (it + SY_STAGES - 1 < total && a.dbg != 2) stage_load(st_load);
         cp_async_commit();
         if (active && a.dbg != 1) {
-            const double *As = ssm + (size_t)st_cur * STAGE;
-            const double *Bs = diag ? As : As + ROWS * SY_LD;
+            const double *As = ssm + (size_t)st_cur * STAGE + aoff;
+            const double *Bs = ssm + (size_t)st_cur * STAGE + boff;
             // one 16-byte load per lane and block feeds TWO k4-steps: lane (fr, fk) takes columns 2fk, 2fk+1 of an 8-wide
             // k-group, .x goes into the first MMA and .y into the second.  Both operands use the same permutation of k
             // inside the group, which a dot product does not see.
@@ -442,6 +459,21 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
         st_load = (st_load + 1 == SY_STAGES) ? 0 : st_load + 1;
     }
     if (!active) return;
+    if (strip_warp) {
+        // strip x this tile's columns -> the strip pair's area, part = this CTA's part (same count of parts by plan)
+        const int snc = a.pairs[a.strip_pair].nc;
+        double *out = a.partial + (size_t)k * a.partial_per_latent + a.pairs[a.strip_pair].out_off + (size_t)part * a.strip_nr * snc;
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+            for (int j = 0; j < NJ; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int row = i * 8 + fr, col = r0 + (base_n + j) * 8 + 2 * fk + e;
+                    if (row < a.strip_nr) out[(size_t)row * snc + col] = acc[i][j][e];
+                }
+        return;
+    }
     double *out = a.partial + (size_t)k * a.partial_per_latent + out_off + (size_t)part * ROWS * COLS;
 #pragma unroll
     for (int i = 0; i < MI; i++)
@@ -463,15 +495,15 @@ __global__ void __launch_bounds__(256, 2) syrk_sum_kernel(const __grid_constant_
 // strip, the finishing kernel adds them in order.
 #define SYS_NB 13
 __global__ void __launch_bounds__(256, 2) syrk_strip_kernel(const __grid_constant__ SyrkArgs a, int pair_index, int warps_total,
-                                                            int ngroups) {
-    const int r0 = a.pairs[pair_index].r0, nr = a.pairs[pair_index].nr, nc = a.pairs[pair_index].nc;
+                                                            int ngroups, int jb0) {
+    const int r0 = a.pairs[pair_index].r0, nr = a.pairs[pair_index].nr, nc = a.pairs[pair_index].nc, pc0 = a.pairs[pair_index].c0;
     const long long out_off = a.pairs[pair_index].out_off;
     const int k = blockIdx.y, sbrow = blockIdx.z / ngroups, grp = blockIdx.z - sbrow * ngroups;
     const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5);      // global warp = part
     const int fr = lane >> 2, fk = lane & 3;
     const int row0 = r0 + sbrow * 8;                              // first row of this strip block row
     const int nbc = (row0 >> 3) + 1;                              // column blocks 0 .. own diagonal block are needed
-    const int jb = grp * SYS_NB;                                  // first column block of this group
+    const int jb = jb0 + grp * SYS_NB;                            // first column block of this group
     const int nb = max(0, min(SYS_NB, nbc - jb));
     if (nb == 0) return;
     const int T = a.T, r = a.r;
@@ -518,8 +550,8 @@ __global__ void __launch_bounds__(256, 2) syrk_strip_kernel(const __grid_constan
     for (int j = 0; j < SYS_NB; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int row = sbrow * 8 + fr, col = (jb + j) * 8 + 2 * fk + e;
-            if (j < nb && row < nr && col < nc) out[(size_t)row * nc + col] = acc[j][e];
+            const int row = sbrow * 8 + fr, col = (jb + j) * 8 + 2 * fk + e - pc0;     // column inside the pair
+            if (j < nb && row < nr && col >= 0 && col < nc) out[(size_t)row * nc + col] = acc[j][e];
         }
 }
 
@@ -820,7 +852,7 @@ LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
 
 // Tile pairs and parts of the PautoSum product for a T x T output and `nslots` slots.  Pairs [0, n_uniform) are
 // full tb x tb tiles (uniform kernel), the rest covers the remainder strip (generic kernel).  Returns tb.
-static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int &grid_uniform, int &grid_generic) {
+static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int &grid_uniform, int &grid_generic, int &jb0_out) {
     const int nblk = (T + 7) / 8;
     int tb = 0;
     // 8-block (64 x 64) tiles: with more, smaller tiles a smaller share of the issued MMAs falls into the half-empty
@@ -845,24 +877,38 @@ static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int 
     const int budget = std::max(std::max(n_uniform, 1), (2 * 148) / std::max(q, 1));    // tile CTAs per latent: about two per SM over all latents
     long long off = 0;
     int part0 = 0;
+    // equal parts for all tile pairs: a diagonal CTA's busiest pipes carry a full tile's load per slot, and the strip
+    // partials written by the diagonal CTAs (below) need the same part count in every column tile
+    const int np_tile = n_uniform ? std::max(1, std::min(budget / n_uniform, nslots)) : 0;
     for (int p = 0; p < n_uniform; p++) {
-        int np = (int)((weights[p] * (long long)budget + wsum / 2) / wsum);
-        np = std::max(1, std::min(np, nslots));
-        a.pairs[p].nparts = np;
+        a.pairs[p].nparts = np_tile;
         a.pairs[p].part0 = part0;
         a.pairs[p].out_off = off;
-        part0 += np;
-        off += (long long)np * a.pairs[p].nr * a.pairs[p].nc;
+        part0 += np_tile;
+        off += (long long)np_tile * a.pairs[p].nr * a.pairs[p].nc;
     }
+    (void)weights; (void)wsum;
     grid_uniform = part0;
     grid_generic = 0;
+    a.strip_pair = -1; a.strip_r0 = 0; a.strip_nr = 0;
+    jb0_out = 0;
     if (s0 < T) {
-        // strip pair: rows [s0, T) against columns [0, T); one part per warp of the strip kernel (8 warps per CTA)
+        const int sr = T - s0, sbrows = (sr + 7) / 8;
+        const int fused = (nt >= 1 && sr <= 16) ? 1 : 0;      // <= 2 block rows: the diagonal CTAs' spare warps take strip x tiles
+        if (fused) {
+            SyrkPair &pm = a.pairs[a.npairs];
+            pm.r0 = s0; pm.nr = sr; pm.c0 = 0; pm.nc = s0; pm.diag = 0; pm.nparts = np_tile; pm.part0 = 0; pm.out_off = off;
+            off += (long long)np_tile * sr * s0;
+            a.strip_pair = a.npairs; a.strip_r0 = s0; a.strip_nr = sr;
+            a.npairs++;
+        }
+        // strip kernel: the whole strip (rows [s0, T) x columns [0, T)), or only its corner [s0, T) x [s0, T) when the
+        // rest is fused into the tile kernel; one part per warp (8 warps per CTA)
         SyrkPair &p = a.pairs[a.npairs];
-        p.r0 = s0; p.nr = T - s0; p.c0 = 0; p.nc = T; p.diag = 0;
-        const int sbrows = (p.nr + 7) / 8;
-        const int ngroups = ((T + 7) / 8 + 12) / 13;                           // column groups of the strip kernel (SYS_NB)
-        int ctas = std::max(1, (2 * 148) / std::max(q * sbrows * ngroups, 1));  // strip CTAs per latent, block row and group
+        p.r0 = s0; p.nr = sr; p.c0 = fused ? s0 : 0; p.nc = T - p.c0; p.diag = 0;
+        jb0_out = p.c0 / 8;
+        const int ngroups = ((T + 7) / 8 - jb0_out + 12) / 13;                 // column groups of the strip kernel (SYS_NB)
+        int ctas = std::max(1, (fused ? 148 : 2 * 148) / std::max(q * sbrows * ngroups, 1));
         ctas = std::max(1, std::min(ctas, (nslots + 7) / 8));
         p.nparts = ctas * 8;
         p.part0 = 0;
@@ -877,15 +923,15 @@ static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int 
 
 size_t pgpfa_i_pautosum_partial_bytes(int q, int T) {
     SyrkArgs a;
-    int nu, gu, gg;
-    syrk_plan(a, T, 1 << 20, q, nu, gu, gg);
+    int nu, gu, gg, jb;
+    syrk_plan(a, T, 1 << 20, q, nu, gu, gg, jb);
     return align_up((size_t)q * a.partial_per_latent * 8);
 }
 
 template <int MI, int NJ, bool V16>
 static int syrk_launch1(const SyrkArgs &a, int grid_x, int q, cudaStream_t st) {
-    constexpr int ROWS = 32 * MI, COLS = 16 * NJ;
-    constexpr int smem = SY_STAGES * (ROWS + COLS) * SY_LD * 8;
+    constexpr int ROWS = 32 * MI, COLS = 16 * NJ, SROWS = 8 * MI;
+    constexpr int smem = SY_STAGES * (ROWS + COLS + SROWS) * SY_LD * 8;
     static bool attr_set = false;
     if (!attr_set) {
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(syrk_sum_kernel<MI, NJ, V16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1030,16 +1076,16 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
         pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
         SyrkArgs a;
         a.Y = Y; a.partial = pauto_partial; a.strideY = (long long)n * r; a.r = r; a.T = T; a.q = q; a.nslots = nslots;
-        int n_uniform = 0, grid_uniform = 0, grid_generic = 0;
-        const int tb = syrk_plan(a, T, nslots, q, n_uniform, grid_uniform, grid_generic);
+        int n_uniform = 0, grid_uniform = 0, grid_generic = 0, jb0 = 0;
+        const int tb = syrk_plan(a, T, nslots, q, n_uniform, grid_uniform, grid_generic, jb0);
         a.first = 0; a.count = n_uniform;          // the tile kernel reads pairs [0, count)
         { const char *e = getenv("PGPFA_SYRK_DBG"); a.dbg = e ? atoi(e) : 0; }
         if (tb == 8) PGPFA_TRY((syrk_launch<2, 4>(a, grid_uniform, q, st)));
         if (grid_generic > 0) {
             const SyrkPair &sp = a.pairs[a.npairs - 1];
-            const int ngroups = ((T + 7) / 8 + SYS_NB - 1) / SYS_NB;
+            const int ngroups = ((T + 7) / 8 - jb0 + SYS_NB - 1) / SYS_NB;
             dim3 gs(grid_generic, q, ((sp.nr + 7) / 8) * ngroups);
-            syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups);
+            syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups, jb0);
             PGPFA_LAUNCH_CHECK();
         }
         dim3 gfin((T + 15) / 16, (T + 15) / 16, q);
