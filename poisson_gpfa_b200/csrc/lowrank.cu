@@ -617,34 +617,63 @@ __global__ void zt_to_dense_lower_kernel(const double *__restrict__ ZT, int nb, 
     }
 }
 
-// Y[(k,t), :] = sum_l P_t[k,l] Yh[(l,t), :]   in place; one CTA handles LR_TB consecutive bins of a slot
+// Y[(k,t), :] = sum_l P_t[k,l] Yh[(l,t), :]   in place; one CTA handles LR_TB consecutive bins of a slot.  The same pass
+// takes this bin group's share of Y^T g (needed by the polishing Newton step): upart[slot][group][c] =
+// sum_{k, t in group} Y[(k,t), c] g[(k,t)], so Y is not streamed a second time for it; lr_usum_kernel adds the groups in
+// order.
 #define LR_TB 8
 template <int Q>
-__global__ void __launch_bounds__(256) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r) {
+__global__ void __launch_bounds__(256) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r,
+                                                     const double *__restrict__ gvec, const int *__restrict__ act,
+                                                     double *__restrict__ upart) {
     __shared__ double Ps[LR_TB][Q * Q];
+    __shared__ double gs[LR_TB][Q];
     const int t0 = blockIdx.x * LR_TB, slot = blockIdx.y;
     for (int i = threadIdx.x; i < LR_TB * Q * Q; i += blockDim.x) {
         const int tl = i / (Q * Q), e = i - tl * Q * Q;
         Ps[tl][e] = (t0 + tl < T) ? Pm[((size_t)slot * Q * Q + e) * T + t0 + tl] : 0.0;
     }
+    if (upart) {
+        const int trial = act ? act[slot] : slot;
+        for (int i = threadIdx.x; i < LR_TB * Q; i += blockDim.x) {
+            const int tl = i / Q, k = i - tl * Q;
+            gs[tl][k] = (t0 + tl < T) ? gvec[(size_t)trial * Q * T + (size_t)k * T + t0 + tl] : 0.0;
+        }
+    }
     __syncthreads();
     double *Ys = Y + (size_t)slot * Q * T * r;
     const int nt = min(LR_TB, T - t0);
-    for (int i = threadIdx.x; i < nt * r; i += blockDim.x) {
-        const int tl = i / r, c = i - tl * r, t = t0 + tl;
-        double v[Q], o[Q];
+    for (int c = threadIdx.x; c < r; c += blockDim.x) {
+        double ua = 0.0;
+        for (int tl = 0; tl < nt; tl++) {
+            const int t = t0 + tl;
+            double v[Q], o[Q];
 #pragma unroll
-        for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
+            for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-            double s = 0.0;
+            for (int k = 0; k < Q; k++) {
+                double s = 0.0;
 #pragma unroll
-            for (int l = 0; l < Q; l++) s += Ps[tl][k * Q + l] * v[l];
-            o[k] = s;
+                for (int l = 0; l < Q; l++) s += Ps[tl][k * Q + l] * v[l];
+                o[k] = s;
+            }
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                Ys[((size_t)k * T + t) * r + c] = o[k];
+                if (upart) ua = fma(o[k], gs[tl][k], ua);
+            }
         }
-#pragma unroll
-        for (int k = 0; k < Q; k++) Ys[((size_t)k * T + t) * r + c] = o[k];
+        if (upart) upart[((size_t)slot * gridDim.x + blockIdx.x) * r + c] = ua;
     }
+}
+
+// u[slot][c] = sum over the bin groups of upart[slot][group][c]
+__global__ void lr_usum_kernel(const double *__restrict__ upart, int ngroups, int r, double *__restrict__ u) {
+    const int slot = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= r) return;
+    double s = 0.0;
+    for (int g = 0; g < ngroups; g++) s += upart[((size_t)slot * ngroups + g) * r + c];
+    u[(size_t)slot * r + c] = s;
 }
 
 // post_vsm[trial][t][k][l] = eps P_t[k,l] + sum_c Y[(k,t),c] Y[(l,t),c]: the q x q Gram matrix of the q rows of Y that
@@ -769,9 +798,10 @@ int lr_launch_bins(const double *W, const int *act, int T, double eps, double *P
     return PGPFA_OK;
 }
 template <int Q>
-int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st) {
+int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st, const double *gvec, const int *act,
+                  double *upart) {
     dim3 grid((T + LR_TB - 1) / LR_TB, nslots);
-    lr_mix_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, T, r);
+    lr_mix_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, T, r, gvec, act, upart);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -1045,9 +1075,16 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
         g.lda = T; g.ldb = r; g.ldc = r; g.cmap = nullptr; g.probs = nullptr; g.dadd_alpha = 0.0;
         PGPFA_TRY(launch_gemm(g, dprobs + qq, (int)tb.yh.size(), tb.yh_tiles, nslots, st));
     }
-    LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st)
-    // ---- polishing Newton step  dx = -Sigma g = -(eps P g + Y (Y^T g))
-    {
+    // ---- polishing Newton step  dx = -Sigma g = -(eps P g + Y (Y^T g)); Y^T g is taken inside the mixing pass (its
+    // per-group partial sums live in G, which is dead once the capacitance matrix is factored)
+    const int ngroups = (T + LR_TB - 1) / LR_TB;
+    if (ngroups <= r) {
+        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, gvec, act, G)
+        dim3 grid((r + 127) / 128, nslots);
+        lr_usum_kernel<<<grid, 128, 0, st>>>(G, ngroups, r, u);
+        PGPFA_LAUNCH_CHECK();
+    } else {
+        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, nullptr, nullptr, nullptr)
         dim3 grid((r + 127) / 128, nslots);
         lr_ytg_kernel<<<grid, 128, 0, st>>>(Y, gvec, act, n, r, u);
         PGPFA_LAUNCH_CHECK();
