@@ -1060,7 +1060,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
         pgpfa_prof_end(h, st);
         if (posterior_pass && use_lr) {
             PGPFA_TRY(pgpfa_i_lowrank_posterior(h, *lr, w.W, w.g, x, w.dx, w.actA, cn, q, T, tol, w.steplen, vsm, vsmGP,
-                                                w.L, w.lr_tables, st, info, pautosum, c0 > 0 ? 1 : 0, x, w.pauto_partial));
+                                                w.L, (size_t)chunk * per, w.lr_tables, st, info, pautosum, c0 > 0 ? 1 : 0, x,
+                                                w.pauto_partial));
             total_factor_trials += cn;
         } else if (posterior_pass) {
             pgpfa_prof_begin(h, PGPFA_PROF_FACTOR, st);

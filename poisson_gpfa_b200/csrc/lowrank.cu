@@ -179,10 +179,13 @@ __global__ void __launch_bounds__(128) lr_bins_kernel(const double *__restrict__
 // 16 through a three-stage ring of padded shared-memory stages filled by cp.async (the k-stride of 20 doubles keeps
 // the 16 lanes of a half-warp on distinct 8-byte banks when they read their DMMA fragments).
 // ---------------------------------------------------------------------------------------------
-enum { GEMM_ADD_IDENTITY = 1, GEMM_SYMMETRIC = 2, GEMM_LOWER_ONLY = 4 };
+enum { GEMM_ADD_IDENTITY = 1, GEMM_SYMMETRIC = 2, GEMM_LOWER_ONLY = 4, GEMM_CAP_SCATTER = 8 };
 struct GemmProb {
     long long a_off, b_off, c_off, s_off, d_off;   // element offsets into the batch's A, B, C, scale, dadd
     int M, N, K, flags;
+    // GEMM_CAP_SCATTER (capacitance matrix as ONE product per latent pair over all slots): row m = a * cap_rl + b of the
+    // product is entry (a, b) of the pair's block, column n is the slot: C[n * strideC + c_off + a * ldc + b]
+    int cap_rl, pad;
 };
 struct GemmArgs {
     const double *A, *B;
@@ -194,6 +197,7 @@ struct GemmArgs {
     const int *cmap;          // optional: C (and nothing else) is indexed by cmap[batch] instead of batch
     const GemmProb *probs;
     double dadd_alpha;
+    int n_override = 0;       // when > 0 it replaces N of every problem (N = slots is only known at launch)
 };
 
 #define GN_STAGES 3
@@ -210,11 +214,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// one 16-wide k-chunk of a warp's MI x NJ live 8x8 blocks (compile-time shape: every issued MMA is a useful one)
+template <int MI, int NJ>
+__device__ __forceinline__ void gemm_nt_chunk(double (&acc)[4][4][2], const double *As, const double *Bs, const double *Ss,
+                                              int wm, int wn, int fr, int fk) {
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+        double a[MI], bb[NJ];
+        const double sv = Ss ? Ss[k4 + fk] : 1.0;
+#pragma unroll
+        for (int i = 0; i < MI; i++) a[i] = As[(wm * 32 + i * 8 + fr) * GN_LD + k4 + fk] * sv;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) bb[j] = Bs[(wn * 32 + j * 8 + fr) * GN_LD + k4 + fk];
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+            for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+}
+
 // K is consumed in chunks of 16 through a GN_STAGES-deep ring of shared-memory stages filled by cp.async, so the
 // global loads of the next two chunks are in flight while the current one is multiplied.
 __global__ void __launch_bounds__(128, 3) gemm_nt_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double gsm[];
-    const GemmProb pr = g.probs[blockIdx.y];
+    GemmProb pr = g.probs[blockIdx.y];
+    if (g.n_override > 0) pr.N = g.n_override;
     const int tm_n = (pr.M + 63) >> 6, tn_n = (pr.N + 63) >> 6;
     if ((int)blockIdx.x >= tm_n * tn_n) return;
     const int tm = blockIdx.x / tn_n, tn = blockIdx.x - tm * tn_n;
@@ -261,22 +285,41 @@ __global__ void __launch_bounds__(128, 3) gemm_nt_kernel(GemmArgs g) {
         if (c + GN_STAGES - 1 < nchunks) stage_load(c + GN_STAGES - 1, (c + GN_STAGES - 1) % GN_STAGES);
         cp_async_commit();
         const double *As = gsm + (size_t)(c % GN_STAGES) * GN_STAGE_DOUBLES, *Bs = As + 64 * GN_LD, *Ss = Bs + 64 * GN_LD;
-        if (mi > 0 && nj > 0) {
-#pragma unroll
-            for (int k4 = 0; k4 < 16; k4 += 4) {
-                double a[4], bb[4];
-                const double sv = sc ? Ss[k4 + fk] : 1.0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[(wm * 32 + i * 8 + fr) * GN_LD + k4 + fk] * sv;
-#pragma unroll
-                for (int j = 0; j < 4; j++) bb[j] = Bs[(wn * 32 + j * 8 + fr) * GN_LD + k4 + fk];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (i < mi && j < nj) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
-            }
+        // The MMAs of a chunk for this warp's mi x nj live blocks, dispatched on the exact shape: a predicated-off
+        // mma.sync still occupies the FP64 pipe (ncu: issued vs predicated-on DMMA counts), and ragged edges are the
+        // normal case here (T = 200 is 3 tiles + 8 rows, rank blocks are 10-110 wide).
+        switch (mi * 5 + nj) {
+#define GN_CASE(MI_, NJ_) case MI_ * 5 + NJ_: gemm_nt_chunk<MI_, NJ_>(acc, As, Bs, sc ? Ss : nullptr, wm, wn, fr, fk); break;
+#define GN_ROW(MI_) GN_CASE(MI_, 1) GN_CASE(MI_, 2) GN_CASE(MI_, 3) GN_CASE(MI_, 4)
+            GN_ROW(1) GN_ROW(2) GN_ROW(3) GN_ROW(4)
+#undef GN_ROW
+#undef GN_CASE
+            default: break;
         }
+    }
+    if (pr.flags & GEMM_CAP_SCATTER) {
+        // transposed epilogue through shared memory: for a slot (column) the rows of the tile are runs of consecutive b,
+        // i.e. contiguous pieces of a row of that slot's capacitance matrix -> coalesced stores
+        __syncthreads();                                   // every warp is done with the operand stages
+        double *Ts = gsm;                                  // [64 columns][65]
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    Ts[(wn * 32 + j * 8 + 2 * fk + e) * 65 + wm * 32 + i * 8 + fr] = acc[i][j][e];
+        __syncthreads();
+        for (int idx = tid; idx < 64 * 64; idx += 128) {
+            const int nl = idx >> 6, ml = idx & 63;
+            const int m = m0 + ml, n = n0 + nl;
+            if (m >= pr.M || n >= pr.N) continue;
+            const int ca = m / pr.cap_rl, cbb = m - ca * pr.cap_rl;
+            double v = Ts[nl * 65 + ml];
+            if ((pr.flags & GEMM_ADD_IDENTITY) && ca == cbb) v += 1.0;
+            g.C[(size_t)n * g.strideC + pr.c_off + (size_t)ca * g.ldc + cbb] = v;
+        }
+        return;
     }
     const size_t cb = (size_t)(g.cmap ? g.cmap[b] : b) * g.strideC + pr.c_off;
     const double *dd = g.dadd ? g.dadd + (size_t)b * g.strideD + pr.d_off : nullptr;
@@ -555,10 +598,56 @@ __global__ void __launch_bounds__(256, 2) syrk_strip_kernel(const __grid_constan
         }
 }
 
+// Corner of the PautoSum product when the strip is fused into the tile kernel: strip rows x strip rows (<= 8 x 8).
+// CTA = one latent x one part of the slots; threads stride (slot, column), 36 running products each, block reduction.
+__global__ void __launch_bounds__(256) syrk_corner_kernel(const __grid_constant__ SyrkArgs a, int pair_index) {
+    __shared__ double red[32];
+    const int k = blockIdx.y, part = blockIdx.x;
+    const int r0 = a.pairs[pair_index].r0, nr = a.pairs[pair_index].nr, nparts = a.pairs[pair_index].nparts;
+    const int s_begin = (int)((long long)a.nslots * part / nparts), s_end = (int)((long long)a.nslots * (part + 1) / nparts);
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = 0.0;
+    const long long items = (long long)(s_end - s_begin) * a.r;
+    for (long long it = threadIdx.x; it < items; it += blockDim.x) {
+        const int slot = s_begin + (int)(it / a.r), c = (int)(it % a.r);
+        const double *col = a.Y + (size_t)slot * a.strideY + ((size_t)k * a.T + r0) * a.r + c;
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i < nr) ? col[(size_t)i * a.r] : 0.0;
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) { acc[idx] = fma(v[i], v[j], acc[idx]); idx++; }
+    }
+    double *out = a.partial + (size_t)k * a.partial_per_latent + a.pairs[pair_index].out_off + (size_t)part * nr * nr;
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            const double sacc = block_sum(acc[idx], red);
+            idx++;
+            if (threadIdx.x == 0 && i < nr) out[i * nr + j] = sacc;
+        }
+}
+
+// dsum[k][t] = sum_slots P_t[k,k] (the eps diag(P) term of post_vsmGP summed over the slots), one CTA per (t, k)
+__global__ void __launch_bounds__(128) syrk_pdiag_kernel(const double *__restrict__ Pm, int nslots, int q, int T,
+                                                         double *__restrict__ dsum) {
+    __shared__ double red[32];
+    const int t = blockIdx.x, k = blockIdx.y;
+    double sacc = 0.0;
+    for (int sl = threadIdx.x; sl < nslots; sl += blockDim.x) sacc += Pm[((size_t)sl * q * q + k * q + k) * T + t];
+    sacc = block_sum(sacc, red);
+    if (threadIdx.x == 0) dsum[(size_t)k * T + t] = sacc;
+}
+
 // PautoSum[k][s][t] (+)= sum_parts partial + [s == t] eps sum_slots P_t[k,k] + sum_slots m[trial,k,s] m[trial,k,t]
 // CTA = 16 x 16 output tile of one latent; the posterior means of 32 slots at a time go through shared memory (each
 // value is then used 16 times), all sums in a fixed order.
-__global__ void __launch_bounds__(256) syrk_finish_kernel(const __grid_constant__ SyrkArgs a, const double *__restrict__ Pm, const double *__restrict__ m,
+__global__ void __launch_bounds__(256) syrk_finish_kernel(const __grid_constant__ SyrkArgs a, const double *__restrict__ dsum, const double *__restrict__ m,
                                                           const int *__restrict__ act, double eps, int accumulate,
                                                           double *__restrict__ Pout) {
     __shared__ double ms[32][17], mt[32][17];
@@ -597,13 +686,25 @@ __global__ void __launch_bounds__(256) syrk_finish_kernel(const __grid_constant_
     }
     if (!in) return;
     v += d0;
-    if (s == t) {
-        double pd = 0.0;
-        for (int sl2 = 0; sl2 < a.nslots; sl2++) pd += Pm[((size_t)sl2 * q * q + k * q + k) * T + t];
-        v += eps * pd;
-    }
+    if (s == t) v += eps * dsum[(size_t)k * T + t];
     double *o = Pout + (size_t)k * T * T + (size_t)s * T + t;
     *o = (accumulate ? *o : 0.0) + v;
+}
+
+// Phi[(a,b)][t] = Ft_k[a][t] Ft_l[b][t] for the latent pair of this problem: the rows of the big capacitance product.
+// grid = (row groups, pairs); the pair's problem entry carries the row offset (a_off / T) and shapes.
+__global__ void __launch_bounds__(256) cap_features_kernel(const double *__restrict__ Ft, const GemmProb *__restrict__ probs,
+                                                           const int2 *__restrict__ kl, int T, double *__restrict__ Phi) {
+    const GemmProb pr = probs[blockIdx.y];
+    const int k = kl[blockIdx.y].x, l = kl[blockIdx.y].y;
+    const double *Fk = Ft + (size_t)k * T * T, *Fl = Ft + (size_t)l * T * T;
+    double *out = Phi + pr.a_off;
+    const long long total = (long long)pr.M * T;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / T), t = (int)(e - (long long)m * T);
+        const int ca = m / pr.cap_rl, cbb = m - ca * pr.cap_rl;
+        out[e] = Fk[(size_t)ca * T + t] * Fl[(size_t)cbb * T + t];
+    }
 }
 
 // Zd[slot][c][a] = (L_b^-1)[c][a] from the packed-upper tiles ZT = L_b^-T (row-major r x r, lower triangular)
@@ -641,29 +742,35 @@ __global__ void __launch_bounds__(256) lr_mix_kernel(double *__restrict__ Y, con
         }
     }
     __syncthreads();
+    extern __shared__ double us[];            // [LR_TB][r] partial Y^T g of each bin (only with upart)
     double *Ys = Y + (size_t)slot * Q * T * r;
     const int nt = min(LR_TB, T - t0);
+    for (int i = threadIdx.x; i < nt * r; i += blockDim.x) {
+        const int tl = i / r, c = i - tl * r, t = t0 + tl;
+        double v[Q], o[Q];
+#pragma unroll
+        for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
+        double ua = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < Q; l++) sacc += Ps[tl][k * Q + l] * v[l];
+            o[k] = sacc;
+        }
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            Ys[((size_t)k * T + t) * r + c] = o[k];
+            ua = fma(o[k], gs[tl][k], ua);
+        }
+        if (upart) us[i] = ua;                   // i = tl * r + c: every (bin, column) has exactly one writer
+    }
+    if (!upart) return;
+    __syncthreads();
     for (int c = threadIdx.x; c < r; c += blockDim.x) {
         double ua = 0.0;
-        for (int tl = 0; tl < nt; tl++) {
-            const int t = t0 + tl;
-            double v[Q], o[Q];
-#pragma unroll
-            for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
-#pragma unroll
-            for (int k = 0; k < Q; k++) {
-                double s = 0.0;
-#pragma unroll
-                for (int l = 0; l < Q; l++) s += Ps[tl][k * Q + l] * v[l];
-                o[k] = s;
-            }
-#pragma unroll
-            for (int k = 0; k < Q; k++) {
-                Ys[((size_t)k * T + t) * r + c] = o[k];
-                if (upart) ua = fma(o[k], gs[tl][k], ua);
-            }
-        }
-        if (upart) upart[((size_t)slot * gridDim.x + blockIdx.x) * r + c] = ua;
+        for (int b = 0; b < nt; b++) ua += us[b * r + c];
+        upart[((size_t)slot * gridDim.x + blockIdx.x) * r + c] = ua;
     }
 }
 
@@ -801,7 +908,10 @@ template <int Q>
 int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st, const double *gvec, const int *act,
                   double *upart) {
     dim3 grid((T + LR_TB - 1) / LR_TB, nslots);
-    lr_mix_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, T, r, gvec, act, upart);
+    const size_t smem = upart ? (size_t)LR_TB * r * sizeof(double) : 0;
+    if (smem > 48 * 1024)
+        PGPFA_CUDA_TRY(cudaFuncSetAttribute(lr_mix_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lr_mix_kernel<Q><<<grid, 256, smem, st>>>(Y, Pm, T, r, gvec, act, upart);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -839,8 +949,10 @@ int launch_gemm(const GemmArgs &g, const GemmProb *dprobs, int nprobs, int max_t
 
 // the three problem tables of a posterior pass: capacitance blocks, Yh per latent, T x T block per latent
 struct LrTables {
-    std::vector<GemmProb> cap, yh, blk;
-    int cap_tiles, yh_tiles, blk_tiles;
+    std::vector<GemmProb> cap, yh, blk, capbig;
+    std::vector<int2> capbig_kl;
+    long long phi_rows;              // rows of the feature matrix of the big capacitance product
+    int cap_tiles, yh_tiles, blk_tiles, capbig_mtiles;
 };
 int max_tiles(const std::vector<GemmProb> &v) {
     int t = 0;
@@ -859,20 +971,39 @@ LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
             pb.s_off = (long long)(k * q + l) * T; pb.d_off = 0;
             pb.M = lr.rank[k]; pb.N = lr.rank[l]; pb.K = T;
             pb.flags = (k == l) ? (GEMM_ADD_IDENTITY | GEMM_LOWER_ONLY) : 0;
+            pb.cap_rl = 0; pb.pad = 0;
             tb.cap.push_back(pb);
+        }
+    // the same blocks as ONE product per latent pair over all slots: rows (a, b), columns = slots, K = T
+    tb.phi_rows = 0;
+    tb.capbig_mtiles = 0;
+    for (int k = 0; k < q; k++)
+        for (int l = 0; l <= k; l++) {
+            if (lr.rank[k] == 0 || lr.rank[l] == 0) continue;
+            GemmProb pb;
+            pb.a_off = tb.phi_rows * T; pb.b_off = (long long)(k * q + l) * T;
+            pb.c_off = (long long)lr.off[k] * r + lr.off[l];
+            pb.s_off = 0; pb.d_off = 0;
+            pb.M = lr.rank[k] * lr.rank[l]; pb.N = 0; pb.K = T;        // N = slots, filled in at launch
+            pb.flags = GEMM_CAP_SCATTER | ((k == l) ? GEMM_ADD_IDENTITY : 0);
+            pb.cap_rl = lr.rank[l]; pb.pad = 0;
+            tb.capbig.push_back(pb);
+            tb.capbig_kl.push_back(make_int2(k, l));
+            tb.phi_rows += pb.M;
+            tb.capbig_mtiles = std::max(tb.capbig_mtiles, (pb.M + 63) / 64);
         }
     for (int l = 0; l < q; l++) {
         GemmProb pb;
         pb.a_off = (long long)l * T * T; pb.b_off = lr.off[l]; pb.c_off = (long long)l * T * r;
         pb.s_off = 0; pb.d_off = 0;
-        pb.M = T; pb.N = r; pb.K = lr.rank[l]; pb.flags = 0;
+        pb.M = T; pb.N = r; pb.K = lr.rank[l]; pb.flags = 0; pb.cap_rl = 0; pb.pad = 0;
         tb.yh.push_back(pb);
     }
     for (int k = 0; k < q; k++) {
         GemmProb pb;
         pb.a_off = (long long)k * T * r; pb.b_off = pb.a_off; pb.c_off = (long long)k * T * T;
         pb.s_off = 0; pb.d_off = (long long)(k * q + k) * T;
-        pb.M = T; pb.N = T; pb.K = r; pb.flags = GEMM_SYMMETRIC;
+        pb.M = T; pb.N = T; pb.K = r; pb.flags = GEMM_SYMMETRIC; pb.cap_rl = 0; pb.pad = 0;
         tb.blk.push_back(pb);
     }
     tb.cap_tiles = max_tiles(tb.cap); tb.yh_tiles = max_tiles(tb.yh); tb.blk_tiles = max_tiles(tb.blk);
@@ -924,7 +1055,7 @@ static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int 
     jb0_out = 0;
     if (s0 < T) {
         const int sr = T - s0, sbrows = (sr + 7) / 8;
-        const int fused = (nt >= 1 && sr <= 16) ? 1 : 0;      // <= 2 block rows: the diagonal CTAs' spare warps take strip x tiles
+        const int fused = (nt >= 1 && sr <= 8) ? 1 : 0;       // one block row: the diagonal CTAs' spare warps take strip x tiles
         if (fused) {
             SyrkPair &pm = a.pairs[a.npairs];
             pm.r0 = s0; pm.nr = sr; pm.c0 = 0; pm.nc = s0; pm.diag = 0; pm.nparts = np_tile; pm.part0 = 0; pm.out_off = off;
@@ -938,9 +1069,9 @@ static int syrk_plan(SyrkArgs &a, int T, int nslots, int q, int &n_uniform, int 
         p.r0 = s0; p.nr = sr; p.c0 = fused ? s0 : 0; p.nc = T - p.c0; p.diag = 0;
         jb0_out = p.c0 / 8;
         const int ngroups = ((T + 7) / 8 - jb0_out + 12) / 13;                 // column groups of the strip kernel (SYS_NB)
-        int ctas = std::max(1, (fused ? 148 : 2 * 148) / std::max(q * sbrows * ngroups, 1));
-        ctas = std::max(1, std::min(ctas, (nslots + 7) / 8));
-        p.nparts = ctas * 8;
+        int ctas = std::max(1, (2 * 148) / std::max(q * sbrows * ngroups, 1));
+        ctas = std::max(1, std::min(ctas, fused ? nslots : (nslots + 7) / 8));
+        p.nparts = fused ? ctas : ctas * 8;             // corner kernel: one part per CTA; strip kernel: one per warp
         p.part0 = 0;
         p.out_off = off;
         off += (long long)p.nparts * p.nr * p.nc;
@@ -995,18 +1126,20 @@ static int syrk_launch(const SyrkArgs &a, int grid_x, int q, cudaStream_t st) {
 int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st) {
     const LrTables tb = lr_tables(lr, q, T);
     const size_t qq = (size_t)q * (q + 1);
-    if (3 * qq * sizeof(GemmProb) > PGPFA_LOWRANK_TABLE_BYTES || 3 * qq * sizeof(GemmProb) > PGPFA_STAGE_BYTES)
-        return PGPFA_ERR_WORKSPACE;
+    const size_t table_bytes = 5 * qq * sizeof(GemmProb);        // 4 problem tables + the (k, l) list of the 4th
+    if (table_bytes > PGPFA_LOWRANK_TABLE_BYTES || table_bytes > PGPFA_STAGE_BYTES) return PGPFA_ERR_WORKSPACE;
     // staged through the handle's pinned buffer: the copy is asynchronous and needs no stream synchronisation (the
     // buffer is rewritten at the earliest by the next E-step, whose predecessor has long consumed it: every E-step
     // ends phase A with a wait for a count produced after this copy)
     PGPFA_CUDA_TRY(cudaEventSynchronize(h->ev_stage));      // previous use of the staging buffer (long complete)
     GemmProb *hs = reinterpret_cast<GemmProb *>(h->stage_h);
-    memset(hs, 0, 3 * qq * sizeof(GemmProb));
+    memset(hs, 0, table_bytes);
     std::copy(tb.cap.begin(), tb.cap.end(), hs);
     std::copy(tb.yh.begin(), tb.yh.end(), hs + qq);
     std::copy(tb.blk.begin(), tb.blk.end(), hs + 2 * qq);
-    PGPFA_CUDA_TRY(cudaMemcpyAsync(probs_dev, hs, 3 * qq * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
+    std::copy(tb.capbig.begin(), tb.capbig.end(), hs + 3 * qq);
+    std::copy(tb.capbig_kl.begin(), tb.capbig_kl.end(), reinterpret_cast<int2 *>(hs + 4 * qq));
+    PGPFA_CUDA_TRY(cudaMemcpyAsync(probs_dev, hs, table_bytes, cudaMemcpyHostToDevice, st));
     PGPFA_CUDA_TRY(cudaEventRecord(h->ev_stage, st));
     return PGPFA_OK;
 }
@@ -1017,8 +1150,9 @@ int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, in
 // time-diagonal blocks (event `ev_means` is recorded here: x / vsm final), then the T x T blocks of every latent.
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
-                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st, int *info,
-                              double *pautosum, int pauto_accumulate, const double *post_mean, double *pauto_partial) {
+                              double *vsm, double *vsmGP, void *area, size_t area_bytes, void *probs_dev, cudaStream_t st,
+                              int *info, double *pautosum, int pauto_accumulate, const double *post_mean,
+                              double *pauto_partial) {
     if (nslots <= 0) return PGPFA_OK;
     const int r = lr.r, n = q * T, nbr = pgpfa_nb(r);
     const long long ltr = pgpfa_ltiles(nbr);
@@ -1036,11 +1170,31 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
     const GemmProb *dprobs = static_cast<const GemmProb *>(probs_dev);
     const size_t qq = (size_t)q * (q + 1);
     const LrTables tb = lr_tables(lr, q, T);
+    // The capacitance blocks are ONE product per latent pair over all slots (rows = entries (a, b) of the block,
+    // columns = slots, K = T) against a feature matrix Phi built per call in the slack of the area: full 64-row tiles
+    // instead of ragged r_k x r_l ones.  The choice depends only on the room in the area, never on the slot count, so
+    // chunked and unchunked solves stay bit-identical (PGPFA_CAP_BIG_MIN is a development switch).
+    double *Phi = (double *)take((size_t)tb.phi_rows * T * 8);
+    static const int cap_big_min = [] { const char *e = getenv("PGPFA_CAP_BIG_MIN"); return e ? atoi(e) : 1; }();
+    const bool cap_big = nslots >= cap_big_min && (size_t)(p - static_cast<unsigned char *>(area)) <= area_bytes &&
+                         !tb.capbig.empty();
 
     // ---- per-bin P, Dt; capacitance matrix G = I + F^T Dt F (lower block triangle, ragged blocks r_k x r_l)
     pgpfa_prof_begin(h, PGPFA_PROF_LOWRANK, st);
     LR_DISPATCH(lr_launch_bins, W, act, T, lr.eps, Pm, Dm, nslots, st)
-    {
+    if (cap_big) {
+        const GemmProb *pb = dprobs + 3 * qq;
+        const int2 *kl = reinterpret_cast<const int2 *>(dprobs + 4 * qq);
+        dim3 gf(32, (unsigned)tb.capbig.size());
+        cap_features_kernel<<<gf, 256, 0, st>>>(lr.Ft, pb, kl, T, Phi);
+        PGPFA_LAUNCH_CHECK();
+        GemmArgs g;
+        g.A = Phi; g.B = Dm; g.C = G; g.scale = nullptr; g.dadd = nullptr;
+        g.strideA = 0; g.strideB = 0; g.strideC = (long long)r * r; g.strideS = 0; g.strideD = 0;
+        g.lda = T; g.ldb = q * q * T; g.ldc = r; g.cmap = nullptr; g.probs = nullptr; g.dadd_alpha = 0.0;
+        g.n_override = nslots;
+        PGPFA_TRY(launch_gemm(g, pb, (int)tb.capbig.size(), tb.capbig_mtiles * ((nslots + 63) / 64), 1, st));
+    } else {
         GemmArgs g;
         g.A = lr.Ft; g.B = lr.Ft; g.C = G; g.scale = Dm; g.dadd = nullptr;
         g.strideA = 0; g.strideB = 0; g.strideC = (long long)r * r; g.strideS = (long long)q * q * T; g.strideD = 0;
@@ -1120,13 +1274,22 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
         if (tb == 8) PGPFA_TRY((syrk_launch<2, 4>(a, grid_uniform, q, st)));
         if (grid_generic > 0) {
             const SyrkPair &sp = a.pairs[a.npairs - 1];
-            const int ngroups = ((T + 7) / 8 - jb0 + SYS_NB - 1) / SYS_NB;
-            dim3 gs(grid_generic, q, ((sp.nr + 7) / 8) * ngroups);
-            syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups, jb0);
+            if (a.strip_nr > 0) {                       // fused strip: only its 8 x 8 corner is left
+                dim3 gc(grid_generic, q);
+                syrk_corner_kernel<<<gc, 256, 0, st>>>(a, a.npairs - 1);
+            } else {
+                const int ngroups = ((T + 7) / 8 - jb0 + SYS_NB - 1) / SYS_NB;
+                dim3 gs(grid_generic, q, ((sp.nr + 7) / 8) * ngroups);
+                syrk_strip_kernel<<<gs, 256, 0, st>>>(a, a.npairs - 1, sp.nparts, ngroups, jb0);
+            }
             PGPFA_LAUNCH_CHECK();
         }
+        double *dsum = Dm;                                   // (q, T) doubles; Dm (slots, q*q, T) is dead after the capacitance GEMM
+        dim3 gpd(T, q);
+        syrk_pdiag_kernel<<<gpd, 128, 0, st>>>(Pm, nslots, q, T, dsum);
+        PGPFA_LAUNCH_CHECK();
         dim3 gfin((T + 15) / 16, (T + 15) / 16, q);
-        syrk_finish_kernel<<<gfin, 256, 0, st>>>(a, Pm, post_mean, act, lr.eps, pauto_accumulate, pautosum);
+        syrk_finish_kernel<<<gfin, 256, 0, st>>>(a, dsum, post_mean, act, lr.eps, pauto_accumulate, pautosum);
         PGPFA_LAUNCH_CHECK();
         pgpfa_prof_end(h, st);
         h->prof_work[PGPFA_PROF_SLICES] += (double)nslots * q * (double)T * (T + 1) * r;

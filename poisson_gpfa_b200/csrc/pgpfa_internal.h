@@ -119,7 +119,7 @@ size_t pgpfa_i_lowrank_bytes_per_slot(int q, int T, int r);
 int pgpfa_i_lowrank_prepare(pgpfa_handle_s *h, const PgpfaLowRank &lr, int q, int T, void *probs_dev, cudaStream_t st);
 int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const double *W, const double *gvec, double *x,
                               double *dx, const int *act, int nslots, int q, int T, double tol, double *steplen,
-                              double *vsm, double *vsmGP, void *area, void *probs_dev, cudaStream_t st,
+                              double *vsm, double *vsmGP, void *area, size_t area_bytes, void *probs_dev, cudaStream_t st,
                               int *info = nullptr, double *pautosum = nullptr, int pauto_accumulate = 0,
                               const double *post_mean = nullptr, double *pauto_partial = nullptr);
 size_t pgpfa_i_pautosum_partial_bytes(int q, int T);
