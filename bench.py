@@ -296,6 +296,8 @@ def run_ours(args):
     e0.record()
     cd_its, tau_evals, newton_its, cg_its, ranks_seen = [], [], [], [], []
     params_in = params
+    start_params, start_x = params.to_numpy_dict(), x0.clone()      # the e2e leg replays the same K iterations
+    n_warm_liks = len(liks)
     for _ in range(args.steps):
         params_in = params
         params, est, lik, info = trials.em_step(params, x0=x0)
@@ -336,17 +338,20 @@ def run_ours(args):
             spot["post_vsmGP"] = rel(est.vsmGP[sel].cpu().numpy(), np.stack([v.transpose(2, 0, 1) for v in ir['post_vsmGP']]))
 
     # ---------------- e2e: the same EM iteration through the public API with HOST buffers every step
-    e2e_steps = max(1, min(args.e2e_steps, args.steps)) if not args.profile_mode else 0
+    # (the SAME K iterations as the timed region: it starts from the parameters and warm start the timed region started
+    # from, so the two numbers are the same work; the rank of the prior factor drifts along the trajectory)
+    e2e_steps = (args.e2e_steps if args.e2e_steps > 0 else args.steps) if not args.profile_mode else 0
     counts_max = float(Y_host.max())
     cdtype = torch.uint8 if counts_max <= 255 else (torch.int16 if counts_max <= 32767 else torch.float64)
     Y_pin = torch.from_numpy(Y_host).to(cdtype).pin_memory()       # the counts as the host holds them (integers)
-    host_params = params.to_numpy_dict()
-    prev = inference._TrialView(est.x.reshape(hi - lo, n)) if e2e_steps else None
-    e2e_t = []
+    e2e_t, e2e_liks = [], []
     h2d = d2h = 0
     exp = inference_experiment(Y_pin, w)
     E2E_WARMUP = 2                                         # untimed: allocate the API path's own buffers, settle the host
     for i in range(e2e_steps + E2E_WARMUP if e2e_steps else 0):
+        if i <= E2E_WARMUP:                                # warm-up steps and the first timed step start from the same state
+            host_params = dict(start_params)
+            prev = inference._TrialView(start_x.reshape(hi - lo, n))
         barrier()
         t0 = time.perf_counter()
         inference.upload_counts(exp)                       # H2D of this step's inputs (pinned -> HBM)
@@ -357,6 +362,7 @@ def run_ours(args):
         barrier()
         if i >= E2E_WARMUP:
             e2e_t.append(time.perf_counter() - t0)
+            e2e_liks.append(float(lik_e))
         h2d = (hi - lo) * N * T * Y_pin.element_size() + (N * q + N + q) * 8
         d2h = (N * q + N + q) * 8 + 8 + 8
     e2e_sec = float(np.mean(e2e_t)) if e2e_t else float("nan")
@@ -436,6 +442,9 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": 1.0 / e2e_sec, "unit": "EM iters/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "same_iterations_as_value": bool(e2e_steps == args.steps),
+                    "post_lik_last": e2e_liks[-1] if e2e_liks else None,
+                    "post_lik_timed_region_same_step": liks[n_warm_liks + e2e_steps - 1] if 0 < e2e_steps <= args.steps else None,
                     "api": "inference.upload_counts (pinned host counts, %s) + inference.laplace + learning.updateParams with "
                            "host numpy parameters in and out each step; the warm start is the previous call's lapOptimRes "
                            "(device-backed)" % str(cdtype).replace("torch.", "")},
@@ -663,7 +672,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trials", type=int, default=0, help="override the trial count (debug only)")
     ap.add_argument("--cpu-trials", type=int, default=2)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = the same K steps as the timed region")
     ap.add_argument("--vi-steps", type=int, default=2)
     ap.add_argument("--online-steps", type=int, default=10)
     ap.add_argument("--skip-cpu", action="store_true")

@@ -136,6 +136,145 @@ extern "C" int pgpfa_hessian_dense(const double *Kinv, const double *W, double d
 extern "C" long long pgpfa_tiles_bytes(int n) { return n > 0 ? pgpfa_ltiles(pgpfa_nb(n)) * PGPFA_TILE * 8 : -1; }
 extern "C" long long pgpfa_dinv_bytes(int n) { return n > 0 ? (long long)pgpfa_nb(n) * PGPFA_TILE * 8 : -1; }
 
+namespace {
+// ---------------------------------------------------------------------------------------------
+// Register-resident SPD inverse for small matrices (n <= SW_NMAX): ONE CTA per matrix, no tile-kernel chain.
+// The T x T prior blocks, the timescale search's candidate matrices and the CG preconditioner are 8-72 matrices of
+// n = T ~ 200: far too few to fill the GPU, so the blocked factor / trtri / lauum chain (12+ dependent launches of
+// latency-bound kernels) costs ~1 ms where the arithmetic is ~30 us of one SM's FP64 pipe.  Here the lower triangle lives
+// in REGISTERS as SW_TS x SW_TS tiles (one thread per tile) and is inverted in place by the symmetric sweep operator
+//     d = A_kk;  A_ij -= A_ik A_kj / d;  A_ik = A_ik / d;  A_kk = -1 / d        (k = 0 .. n-1  ->  -A^-1)
+// whose pivots are those of the Cholesky / LDL^T factorisation (logdet = sum log d).  Per step the column k goes
+// through shared memory (double-buffered: one __syncthreads per step) and every thread does SW_TS^2 DFMAs on registers; row
+// and column k are folded into the same rank-1 form (u_k = 1 - 1/d, w_k = d - 1, then A_kk -= 2) so there is no
+// per-element select.
+// ---------------------------------------------------------------------------------------------
+#define SW_TS 10                       // tile edge: 100 doubles of the matrix per thread
+#define SW_THREADS 256                 // 2 warps per SM sub-partition -> 255 registers per thread
+#define SW_NMAX 220                    // 22 * 23 / 2 = 253 tiles
+
+__global__ void __launch_bounds__(SW_THREADS, 1) spd_sweep_kernel(const double *__restrict__ A, int n, double *__restrict__ Ainv,
+                                                                  double *__restrict__ logdet, int *__restrict__ info) {
+    constexpr int TS = SW_TS;
+    __shared__ __align__(16) double cbuf[2][SW_NMAX + 4];      // column k, then 1 / d_k and d_k
+    __shared__ double piv[SW_NMAX];
+    __shared__ double red[SW_THREADS / 32];
+    __shared__ int s_bad;
+    const int nt = (n + TS - 1) / TS, ntiles = nt * (nt + 1) / 2, NP = nt * TS;
+    const int t = threadIdx.x;
+    const bool live = t < ntiles;
+    int ti = 0, tj = 0;
+    if (live) {
+        ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        tj = t - ti * (ti + 1) / 2;
+    }
+    const double *Ab = A + (size_t)blockIdx.x * n * n;
+    double a[TS][TS];
+#pragma unroll
+    for (int r = 0; r < TS; r++)
+#pragma unroll
+        for (int c = 0; c < TS; c++) {
+            const int i = ti * TS + r, j = tj * TS + c;
+            a[r][c] = (live && i < n && j < n) ? Ab[(size_t)i * n + j] : (i == j ? 1.0 : 0.0);   // identity padding
+        }
+    if (t == 0) s_bad = 0;
+    if (live && tj == 0) {
+#pragma unroll
+        for (int r = 0; r < TS; r++) cbuf[0][ti * TS + r] = a[r][0];
+        if (ti == 0) { cbuf[0][NP] = 1.0 / a[0][0]; cbuf[0][NP + 1] = a[0][0]; piv[0] = a[0][0]; }
+    }
+    __syncthreads();
+    for (int tk = 0; tk < nt; tk++) {
+#pragma unroll
+        for (int kk = 0; kk < TS; kk++) {
+            const int k = tk * TS + kk;
+            const int kn = (kk + 1) % TS;                       // in-tile index of column k + 1
+            const int tkn = kk + 1 == TS ? tk + 1 : tk;         // and its tile
+            const double *cc = cbuf[k & 1];
+            double *cn = cbuf[(k + 1) & 1];
+            if (live) {
+                const double dinv = cc[NP], d = cc[NP + 1];
+                double w[TS];
+#pragma unroll
+                for (int c = 0; c < TS; c++) w[c] = cc[tj * TS + c];
+                if (tj == tk) w[kk] = d - 1.0;
+                const bool rowk = ti == tk;
+                // (1) the entries column k + 1 is read from go first, so that its publication (and the owner's
+                //     reciprocal of the next pivot) overlaps the bulk of the update instead of preceding the barrier
+#pragma unroll
+                for (int r = 0; r < TS; r++) {
+                    double u = cc[ti * TS + r] * dinv;
+                    if (r == kk && rowk) u = 1.0 - dinv;
+                    a[r][kn] = fma(-u, w[kn], a[r][kn]);
+                    if (r == kn) {
+#pragma unroll
+                        for (int c = 0; c < TS; c++)
+                            if (c != kn) a[r][c] = fma(-u, w[c], a[r][c]);
+                    }
+                }
+                if (k + 1 < NP) {
+                    if (tj == tkn) {
+#pragma unroll
+                        for (int r = 0; r < TS; r++) cn[ti * TS + r] = a[r][kn];
+                        if (ti == tkn) {
+                            const double dn = a[kn][kn];
+                            cn[NP] = 1.0 / dn; cn[NP + 1] = dn; piv[k + 1] = dn;
+                        }
+                    } else if (ti == tkn) {
+#pragma unroll
+                        for (int c = 0; c < TS; c++) cn[tj * TS + c] = a[kn][c];
+                    }
+                }
+                // (2) the rest of the tile
+#pragma unroll
+                for (int r = 0; r < TS; r++) {
+                    if (r == kn) continue;
+                    double u = cc[ti * TS + r] * dinv;
+                    if (r == kk && rowk) u = 1.0 - dinv;
+#pragma unroll
+                    for (int c = 0; c < TS; c++)
+                        if (c != kn) a[r][c] = fma(-u, w[c], a[r][c]);
+                }
+                if (rowk && tj == tk) a[kk][kk] -= 2.0;
+            }
+            __syncthreads();
+        }
+    }
+    if (live) {
+        double *Ob = Ainv + (size_t)blockIdx.x * n * n;
+#pragma unroll
+        for (int r = 0; r < TS; r++)
+#pragma unroll
+            for (int c = 0; c < TS; c++) {
+                const int i = ti * TS + r, j = tj * TS + c;
+                if (i < n && j < n && (ti != tj || r >= c)) {
+                    Ob[(size_t)i * n + j] = -a[r][c];
+                    Ob[(size_t)j * n + i] = -a[r][c];
+                }
+            }
+    }
+    // log-determinant and the first non-positive pivot from the stored pivots
+    double ld = 0.0;
+    for (int k = t; k < n; k += blockDim.x) {
+        const double d = piv[k];
+        if (!(d > 0.0)) atomicMax(&s_bad, n - k);          // smallest k wins
+        ld += log(d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    if ((t & 31) == 0) red[t >> 5] = ld;
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) tot += red[wv];
+        if (logdet) logdet[blockIdx.x] = tot;
+        if (info) info[blockIdx.x] = s_bad ? n - s_bad + 1 : 0;
+    }
+}
+}  // namespace
+
 extern "C" long long pgpfa_spd_inverse_workspace_bytes(int batch, int n) {
     if (batch <= 0 || n <= 0) return -1;
     const int nb = pgpfa_nb(n);
@@ -160,6 +299,13 @@ extern "C" int pgpfa_spd_inverse_batched(const double *A, int batch, int n, doub
     if (!A || !Ainv || batch <= 0 || n <= 0) return PGPFA_ERR_ARG;
     InvWs w;
     PGPFA_TRY(carve_inv_ws(workspace, ws_bytes, batch, n, w));
+    static const bool sweep_on = [] { const char *e = getenv("PGPFA_SPD_SWEEP"); return !e || atoi(e) != 0; }();
+    if (sweep_on && n <= SW_NMAX) {                 // one register-resident CTA per matrix
+        const int nt = (n + SW_TS - 1) / SW_TS, threads = ((nt * (nt + 1) / 2 + 31) / 32) * 32;
+        spd_sweep_kernel<<<batch, threads, 0, st>>>(A, n, Ainv, logdet, info);
+        PGPFA_LAUNCH_CHECK();
+        return PGPFA_OK;
+    }
     const int npairs = pgpfa_i_num_pairs(1, n, true);
     PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, 1, n, true, st));        // generated on the device: no host temporary, no sync
     if (info) PGPFA_CUDA_TRY(cudaMemsetAsync(info, 0, (size_t)batch * 4, st));
