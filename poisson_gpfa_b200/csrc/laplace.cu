@@ -99,9 +99,12 @@ __global__ void __launch_bounds__(128) prior_apply_kernel(const double *__restri
             }
 }
 
-// fused rates + objective + gradient + per-bin Hessian blocks; one CTA per trial, thread <-> bin
-template <int Q>
-__global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restrict__ x, const double *__restrict__ Kx,
+// fused rates + objective + gradient + per-bin Hessian blocks; one CTA per trial, thread <-> bin.
+// The kernel is bound by FP64 latency, not by its pipe (ncu r02c: pipe 30 % busy at one 8-warp CTA per SM, 166
+// registers): BS = 224 threads cover T <= 224 bins with one bin per thread and leave room for TWO CTAs per SM
+// (2 x 224 x 146 registers); HAS_OFF drops the variational path's offsets from the Laplace instantiation.
+template <int Q, bool HAS_OFF, int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) laplace_eval_kernel(const double *__restrict__ x, const double *__restrict__ Kx,
                                                            const double *__restrict__ y, const double *__restrict__ C,
                                                            const double *__restrict__ d, const double *__restrict__ off,
                                                            const int *act, int N, int T,
@@ -128,16 +131,24 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
         const int yrow = loo.ymap ? loo.ymap[trial] : trial;
         const int skip = loo.excl ? loo.excl[trial] : -1;
         const double *yp = y + (size_t)yrow * N * T + t;
-        const double *op = off ? off + (size_t)trial * N * T + t : nullptr;
-        // neurons in groups of four: the four counts (and log-rate offsets) are in flight together, the row of C of a
-        // neuron is read once from shared memory into registers (every thread reads the same address: broadcast)
+        const double *op = HAS_OFF ? off + (size_t)trial * N * T + t : nullptr;
+        // neurons in groups of four: the four counts (and log-rate offsets) of the NEXT group are in flight while the
+        // current one is computed; the row of C of a neuron is read once from shared memory into registers (every
+        // thread reads the same address: broadcast)
+        double yn[4], on[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            yn[u] = (u < N) ? yp[(size_t)u * T] : 0.0;
+            on[u] = (HAS_OFF && u < N) ? op[(size_t)u * T] : 0.0;
+        }
         for (int n0 = 0; n0 < N; n0 += 4) {
             double yv[4], ov[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int n = n0 + u;
-                yv[u] = (n < N) ? yp[(size_t)n * T] : 0.0;
-                ov[u] = (op && n < N) ? op[(size_t)n * T] : 0.0;
+                yv[u] = yn[u]; ov[u] = on[u];
+                const int n = n0 + 4 + u;
+                yn[u] = (n < N) ? yp[(size_t)n * T] : 0.0;
+                on[u] = (HAS_OFF && n < N) ? op[(size_t)n * T] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(256) laplace_eval_kernel(const double *__restr
 #pragma unroll
                 for (int k = 0; k < Q; k++) h = fma(c[k], xk[k], h);
                 // variational path: rates carry the extra log-offset s[n,t] = 0.5 c_n^T Sigma_tt c_n
-                const double lam = exp(h + ov[u]);
+                const double lam = exp(HAS_OFF ? h + ov[u] : h);
                 fl += fma(-yv[u], h, lam);
                 const double r = lam - yv[u];
                 int idx = 0;
@@ -635,9 +646,18 @@ int launch_eval(const double *x, const double *Kx, const double *y, const double
                 const int *act, int nslots, int N, int T, double *f, double *g, double *W, cudaStream_t st, LooMap loo,
                 const int *cnt) {
     const size_t smem = (size_t)(N * Q + N) * sizeof(double);
-    if (smem > 48 * 1024)
-        PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    laplace_eval_kernel<Q><<<nslots, 256, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W, loo, cnt);
+#define EVAL_LAUNCH(OFF_, BS_, MINB_)                                                                                      \
+    do {                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                              \
+            PGPFA_CUDA_TRY(cudaFuncSetAttribute(laplace_eval_kernel<Q, OFF_, BS_, MINB_>,                                  \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        laplace_eval_kernel<Q, OFF_, BS_, MINB_><<<nslots, BS_, smem, st>>>(x, Kx, y, C, d, off, act, N, T, f, g, W, loo,  \
+                                                                            cnt);                                          \
+    } while (0)
+    const bool small = 3 * smem <= 200 * 1024;
+    if (off) { if (small) EVAL_LAUNCH(true, 128, 3); else EVAL_LAUNCH(true, 256, 1); }
+    else     { if (small) EVAL_LAUNCH(false, 128, 3); else EVAL_LAUNCH(false, 256, 1); }
+#undef EVAL_LAUNCH
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
