@@ -723,53 +723,84 @@ __global__ void zt_to_dense_lower_kernel(const double *__restrict__ ZT, int nb, 
 // sum_{k, t in group} Y[(k,t), c] g[(k,t)], so Y is not streamed a second time for it; lr_usum_kernel adds the groups in
 // order.
 #define LR_TB 8
+struct LrOffs { int off[PGPFA_QMAX]; };      // first column of each latent in the rank-r factor
+// One warp per bin.  Per 8-column chunk the mixing is the product  Y^T[c][k] = sum_l Yh^T[c][l] P_t[k][l]  on DMMA.8x8x4:
+// the chunk of Yh is the A operand (row = column c of Y, loaded as 64-byte runs of the latents' rows), P_t sits in the B
+// fragments for the whole row sweep, and the C fragment has lane (fr, fk) holding column c0 + fr of latents 2 fk, 2 fk + 1
+// - so the eight lanes of an fk write 64 contiguous bytes of one row of Y.  (The scalar form spent 64 shared-memory
+// reads and 64 DFMAs per output element; a row-major C fragment wrote 8-byte pieces at a 16-byte stride, 2.5x the sectors.)
 template <int Q>
 __global__ void __launch_bounds__(256) lr_mix_kernel(double *__restrict__ Y, const double *__restrict__ Pm, int T, int r,
                                                      const double *__restrict__ gvec, const int *__restrict__ act,
-                                                     double *__restrict__ upart) {
-    __shared__ double Ps[LR_TB][Q * Q];
-    __shared__ double gs[LR_TB][Q];
-    const int t0 = blockIdx.x * LR_TB, slot = blockIdx.y;
-    for (int i = threadIdx.x; i < LR_TB * Q * Q; i += blockDim.x) {
-        const int tl = i / (Q * Q), e = i - tl * Q * Q;
-        Ps[tl][e] = (t0 + tl < T) ? Pm[((size_t)slot * Q * Q + e) * T + t0 + tl] : 0.0;
-    }
-    if (upart) {
-        const int trial = act ? act[slot] : slot;
-        for (int i = threadIdx.x; i < LR_TB * Q; i += blockDim.x) {
-            const int tl = i / Q, k = i - tl * Q;
-            gs[tl][k] = (t0 + tl < T) ? gvec[(size_t)trial * Q * T + (size_t)k * T + t0 + tl] : 0.0;
-        }
-    }
-    __syncthreads();
+                                                     double *__restrict__ upart, const LrOffs offs) {
+    constexpr int NB = (Q + 7) / 8, KS = (Q + 3) / 4;
     extern __shared__ double us[];            // [LR_TB][r] partial Y^T g of each bin (only with upart)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    const int slot = blockIdx.y, t0 = blockIdx.x * LR_TB, t = t0 + warp;
     double *Ys = Y + (size_t)slot * Q * T * r;
-    const int nt = min(LR_TB, T - t0);
-    for (int i = threadIdx.x; i < nt * r; i += blockDim.x) {
-        const int tl = i / r, c = i - tl * r, t = t0 + tl;
-        double v[Q], o[Q];
+    if (t < T) {
+        double pb[NB][KS], g0[NB], g1[NB];
+        const int trial = (upart && act) ? act[slot] : slot;
 #pragma unroll
-        for (int l = 0; l < Q; l++) v[l] = Ys[((size_t)l * T + t) * r + c];
-        double ua = 0.0;
+        for (int nb = 0; nb < NB; nb++) {
+            const int k = nb * 8 + fr;                  // B fragment: B[kdim = l][n = k] = P_t[k][l]
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int l = 0; l < Q; l++) sacc += Ps[tl][k * Q + l] * v[l];
-            o[k] = sacc;
+            for (int ks = 0; ks < KS; ks++) {
+                const int l = ks * 4 + fk;
+                pb[nb][ks] = (k < Q && l < Q) ? Pm[((size_t)slot * Q * Q + k * Q + l) * T + t] : 0.0;
+            }
+            const int kc = nb * 8 + 2 * fk;             // C fragment columns of this lane: latents kc, kc + 1
+            g0[nb] = (upart && kc < Q) ? gvec[(size_t)trial * Q * T + (size_t)kc * T + t] : 0.0;
+            g1[nb] = (upart && kc + 1 < Q) ? gvec[(size_t)trial * Q * T + (size_t)(kc + 1) * T + t] : 0.0;
         }
+        int offl[KS];
+        const double *arow[KS];
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-            Ys[((size_t)k * T + t) * r + c] = o[k];
-            ua = fma(o[k], gs[tl][k], ua);
+        for (int ks = 0; ks < KS; ks++) {
+            const int l = ks * 4 + fk;
+            offl[ks] = l < Q ? offs.off[l] : r;                      // columns left of off_l are structural zeros
+            arow[ks] = Ys + ((size_t)(l < Q ? l : 0) * T + t) * r;
         }
-        if (upart) us[i] = ua;                   // i = tl * r + c: every (bin, column) has exactly one writer
+#pragma unroll 4
+        for (int c0 = 0; c0 < r; c0 += 8) {
+            const int c = c0 + fr;                       // column of this lane in the A and the C fragment
+            double av[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                av[ks] = 0.0;
+                if (c >= offl[ks] && c < r) av[ks] = arow[ks][c];
+            }
+            double acc[NB][2];
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) {
+                acc[nb][0] = 0.0; acc[nb][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) dmma884(acc[nb][0], acc[nb][1], av[ks], pb[nb][ks]);
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) {
+                const int kc = nb * 8 + 2 * fk;
+                if (c < r) {
+                    if (kc < Q) Ys[((size_t)kc * T + t) * r + c] = acc[nb][0];
+                    if (kc + 1 < Q) Ys[((size_t)(kc + 1) * T + t) * r + c] = acc[nb][1];
+                }
+                s = fma(acc[nb][0], g0[nb], s);
+                s = fma(acc[nb][1], g1[nb], s);
+            }
+            if (upart) {
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (fk == 0 && c < r) us[warp * r + c] = s;
+            }
+        }
     }
     if (!upart) return;
     __syncthreads();
+    const int nt = min(LR_TB, T - t0);
     for (int c = threadIdx.x; c < r; c += blockDim.x) {
         double ua = 0.0;
-        for (int b = 0; b < nt; b++) ua += us[b * r + c];
+        for (int bb = 0; bb < nt; bb++) ua += us[bb * r + c];
         upart[((size_t)slot * gridDim.x + blockIdx.x) * r + c] = ua;
     }
 }
@@ -906,12 +937,12 @@ int lr_launch_bins(const double *W, const int *act, int T, double eps, double *P
 }
 template <int Q>
 int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStream_t st, const double *gvec, const int *act,
-                  double *upart) {
+                  double *upart, const LrOffs &offs) {
     dim3 grid((T + LR_TB - 1) / LR_TB, nslots);
     const size_t smem = upart ? (size_t)LR_TB * r * sizeof(double) : 0;
     if (smem > 48 * 1024)
         PGPFA_CUDA_TRY(cudaFuncSetAttribute(lr_mix_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lr_mix_kernel<Q><<<grid, 256, smem, st>>>(Y, Pm, T, r, gvec, act, upart);
+    lr_mix_kernel<Q><<<grid, 256, smem, st>>>(Y, Pm, T, r, gvec, act, upart, offs);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -994,9 +1025,12 @@ LrTables lr_tables(const PgpfaLowRank &lr, int q, int T) {
         }
     for (int l = 0; l < q; l++) {
         GemmProb pb;
-        pb.a_off = (long long)l * T * T; pb.b_off = lr.off[l]; pb.c_off = (long long)l * T * r;
+        // Z = L^-1 is lower triangular: Z[c][off_l + a] = 0 for c < off_l, so latent l has no columns c < off_l
+        // (never computed, never stored; the mixing pass reads them as zeros)
+        pb.a_off = (long long)l * T * T; pb.b_off = lr.off[l] + (long long)lr.off[l] * r;
+        pb.c_off = (long long)l * T * r + lr.off[l];
         pb.s_off = 0; pb.d_off = 0;
-        pb.M = T; pb.N = r; pb.K = lr.rank[l]; pb.flags = 0; pb.cap_rl = 0; pb.pad = 0;
+        pb.M = T; pb.N = r - lr.off[l]; pb.K = lr.rank[l]; pb.flags = 0; pb.cap_rl = 0; pb.pad = 0;
         tb.yh.push_back(pb);
     }
     for (int k = 0; k < q; k++) {
@@ -1232,13 +1266,15 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
     // ---- polishing Newton step  dx = -Sigma g = -(eps P g + Y (Y^T g)); Y^T g is taken inside the mixing pass (its
     // per-group partial sums live in G, which is dead once the capacitance matrix is factored)
     const int ngroups = (T + LR_TB - 1) / LR_TB;
+    LrOffs offs;
+    for (int l = 0; l < PGPFA_QMAX; l++) offs.off[l] = l < q ? lr.off[l] : 0;
     if (ngroups <= r) {
-        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, gvec, act, G)
+        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, gvec, act, G, offs)
         dim3 grid((r + 127) / 128, nslots);
         lr_usum_kernel<<<grid, 128, 0, st>>>(G, ngroups, r, u);
         PGPFA_LAUNCH_CHECK();
     } else {
-        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, nullptr, nullptr, nullptr)
+        LR_DISPATCH(lr_launch_mix, Y, Pm, T, r, nslots, st, nullptr, nullptr, nullptr, offs)
         dim3 grid((r + 127) / 128, nslots);
         lr_ytg_kernel<<<grid, 128, 0, st>>>(Y, gvec, act, n, r, u);
         PGPFA_LAUNCH_CHECK();
