@@ -818,14 +818,20 @@ __global__ void lr_usum_kernel(const double *__restrict__ upart, int ngroups, in
 // belong to bin t, one warp per bin on the FP64 tensor pipe.  For m8n8k4 the A fragment (row = lane/4, k = lane%4) of a
 // matrix and the B fragment (k = lane%4, col = lane/4) of its transpose are the same register, so one 8-byte load per
 // lane and k-step feeds the MMA; Y is streamed from HBM exactly once.
-template <int Q>
+template <int Q, bool STEP>
 __global__ void __launch_bounds__(256) lr_vsm_kernel(const double *__restrict__ Y, const double *__restrict__ Pm,
                                                      const int *__restrict__ act, int T, int r, double eps,
-                                                     double *__restrict__ vsm) {
+                                                     double *__restrict__ vsm, const double *__restrict__ u,
+                                                     const double *__restrict__ gvec, double *__restrict__ dx) {
     constexpr int QB = (Q + 7) / 8;
     const int slot = blockIdx.y, trial = act ? act[slot] : slot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 8 + warp;
+    extern __shared__ double u_s[];                       // Y^T g of the slot (only with dx), zero-padded to 4
+    if (STEP) {
+        for (int c = threadIdx.x; c < ((r + 3) & ~3); c += blockDim.x) u_s[c] = c < r ? u[(size_t)slot * r + c] : 0.0;
+        __syncthreads();
+    }
     if (t >= T) return;
     const int fr = lane >> 2, fk = lane & 3;
     const double *rowp[QB];
@@ -836,16 +842,39 @@ __global__ void __launch_bounds__(256) lr_vsm_kernel(const double *__restrict__ 
         rowok[bi] = row < Q;
         rowp[bi] = Y + ((size_t)slot * Q * T + (size_t)(rowok[bi] ? row : 0) * T + t) * r;
     }
+    // With dx the same sweep over the rows of Y also takes the polishing Newton step of this bin,
+    // dx[(k,t)] = -(eps (P_t g_t)_k + Y[(k,t),:] u): the rows are streamed once for both.
     double acc[QB][QB][2] = {};
+    double su[QB] = {};
 #pragma unroll 4
     for (int k0 = 0; k0 < r; k0 += 4) {
         double a[QB];
 #pragma unroll
         for (int bi = 0; bi < QB; bi++) a[bi] = (rowok[bi] && k0 + fk < r) ? rowp[bi][k0 + fk] : 0.0;
+        if (STEP) {
+            const double uv = u_s[k0 + fk];
+#pragma unroll
+            for (int bi = 0; bi < QB; bi++) su[bi] = fma(a[bi], uv, su[bi]);
+        }
 #pragma unroll
         for (int bi = 0; bi < QB; bi++)
 #pragma unroll
             for (int bj = 0; bj < QB; bj++) dmma884(acc[bi][bj][0], acc[bi][bj][1], a[bi], a[bj]);
+    }
+    if (STEP) {
+#pragma unroll
+        for (int bi = 0; bi < QB; bi++) {
+            su[bi] += __shfl_xor_sync(0xffffffffu, su[bi], 1);
+            su[bi] += __shfl_xor_sync(0xffffffffu, su[bi], 2);
+            const int k = bi * 8 + fr;
+            if (fk == 0 && k < Q) {
+                double pg = 0.0;
+#pragma unroll
+                for (int l = 0; l < Q; l++)
+                    pg += Pm[((size_t)slot * Q * Q + k * Q + l) * T + t] * gvec[(size_t)trial * Q * T + (size_t)l * T + t];
+                dx[(size_t)trial * Q * T + (size_t)k * T + t] = -(eps * pg + su[bi]);
+            }
+        }
     }
     double *out = vsm + ((size_t)trial * T + t) * Q * Q;
 #pragma unroll
@@ -948,9 +977,10 @@ int lr_launch_mix(double *Y, const double *Pm, int T, int r, int nslots, cudaStr
 }
 template <int Q>
 int lr_launch_vsm(const double *Y, const double *Pm, const int *act, int T, int r, double eps, double *vsm, int nslots,
-                  cudaStream_t st) {
+                  cudaStream_t st, const double *u, const double *gvec, double *dx) {
     dim3 grid((T + 7) / 8, nslots);
-    lr_vsm_kernel<Q><<<grid, 256, 0, st>>>(Y, Pm, act, T, r, eps, vsm);
+    if (dx) lr_vsm_kernel<Q, true><<<grid, 256, (size_t)((r + 3) & ~3) * sizeof(double), st>>>(Y, Pm, act, T, r, eps, vsm, u, gvec, dx);
+    else lr_vsm_kernel<Q, false><<<grid, 256, 0, st>>>(Y, Pm, act, T, r, eps, vsm, u, gvec, dx);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -1279,10 +1309,13 @@ int pgpfa_i_lowrank_posterior(pgpfa_handle_s *h, const PgpfaLowRank &lr, const d
         lr_ytg_kernel<<<grid, 128, 0, st>>>(Y, gvec, act, n, r, u);
         PGPFA_LAUNCH_CHECK();
     }
-    LR_DISPATCH(lr_launch_step, Y, u, Pm, gvec, act, T, r, lr.eps, dx, nslots, st)
+    // ---- the step and the per-bin q x q slices come out of ONE sweep over Y
+    if (vsm) {
+        LR_DISPATCH(lr_launch_vsm, Y, Pm, act, T, r, lr.eps, vsm, nslots, st, u, gvec, dx)
+    } else {
+        LR_DISPATCH(lr_launch_step, Y, u, Pm, gvec, act, T, r, lr.eps, dx, nslots, st)
+    }
     PGPFA_TRY(pgpfa_i_polish(x, dx, act, n, 1e3 * tol, steplen, nslots, st));
-    // ---- slices
-    if (vsm) LR_DISPATCH(lr_launch_vsm, Y, Pm, act, T, r, lr.eps, vsm, nslots, st)
     PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
     pgpfa_prof_end(h, st);
     if (vsmGP) {
