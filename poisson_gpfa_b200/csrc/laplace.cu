@@ -25,15 +25,18 @@ namespace {
 // in L2 (q T^2 doubles); the vectors are gathered through the active list.
 #define PA_TS 64
 #define PA_TN 32
+// With out2 the grid covers 2 q matrices: matrix m >= q is applied to the SAME vectors (latent m - q) and lands in out2
+// (the CG loop's z = M^-1 r and K^-1 M^-1 r in one launch).
 __global__ void __launch_bounds__(128) prior_apply_kernel(const double *__restrict__ Kmat, const double *__restrict__ v,
                                                           double *__restrict__ out, const int *act, int nslots, int q,
-                                                          int T, const int *__restrict__ cnt) {
+                                                          int T, const int *__restrict__ cnt, double *__restrict__ out2) {
     __shared__ double As[2][PA_TS][20];
     __shared__ double Bs[2][16][36];
     __shared__ int trial[PA_TN];
-    const int k = blockIdx.x, s0 = blockIdx.y * PA_TS, n0 = blockIdx.z * PA_TN;
+    const int m = blockIdx.x, k = m < q ? m : m - q, s0 = blockIdx.y * PA_TS, n0 = blockIdx.z * PA_TN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const int fr = lane >> 2, fk = lane & 3;
+    if (m >= q) out = out2;
     if (cnt) {                                   // device-resident slot count (grid sized by a host upper bound)
         nslots = min(nslots, *cnt);
         if (n0 >= nslots) return;
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(128) prior_apply_kernel(const double *__restri
         trial[tid] = slot < nslots ? (act ? act[slot] : slot) : -1;
     }
     __syncthreads();
-    const double *Kk = Kmat + (size_t)k * T * T;
+    const double *Kk = Kmat + (size_t)m * T * T;
     // this thread's share of a chunk: 8 elements of A (row ar + 8 j, column ac), 4 of B (trial bn + 8 j, bin bc)
     const int ar = tid >> 4, ac = tid & 15, bn = tid >> 4, bc = tid & 15;
     const double *bsrc[4];
@@ -484,24 +487,6 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict_
     }
 }
 
-// p = z + beta p (beta = 0 on the first call), rz = r.z
-template <int Q>
-__global__ void __launch_bounds__(256) pcg_dir_kernel(const double *__restrict__ r, const double *__restrict__ z,
-                                                      double *__restrict__ p, const int *act, int T, int first,
-                                                      double *__restrict__ pcg_s, const int *__restrict__ cnt) {
-    __shared__ double red[32];
-    if (cnt && (int)blockIdx.x >= *cnt) return;
-    const int trial = act ? act[blockIdx.x] : blockIdx.x;
-    const size_t base = (size_t)trial * Q * T;
-    double rz = 0.0;
-    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) rz += r[base + i] * z[base + i];
-    rz = block_sum(rz, red);
-    const double beta = first ? 0.0 : rz / pcg_s[trial * 4 + 0];
-    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) p[base + i] = z[base + i] + (first ? 0.0 : beta * p[base + i]);
-    __syncthreads();
-    if (threadIdx.x == 0) pcg_s[trial * 4 + 0] = rz;
-}
-
 // The CG list is compacted by the LAST CTA of the step kernel to finish (ticket counter + __threadfence, the
 // "threadFenceReduction" pattern) instead of by a launch of its own: one launch and ~7 us less per CG iteration.
 struct CgTail {
@@ -510,13 +495,18 @@ struct CgTail {
     int *prog;              // progress word in mapped pinned memory (or nullptr)
 };
 
-// Hp = Kp + W p ; alpha = rz / p.Hp ; delta += alpha p ; r -= alpha Hp ; converged when |r| <= eta |b|
+// One CG iteration per launch.  The preceding stacked prior_apply left z = M^-1 r and Nr = K^-1 M^-1 r (in Hp's buffer:
+// it is read here before Hp is written, per trial, with a barrier in between).  M^-1 and K^-1 are functions of the same
+// K_k, so K^-1 p follows the direction's own recurrence and is never multiplied out:
+//   rz = r.z ; beta = rz / rz_old ; p = z + beta p ; Kp = Nr + beta Kp        (beta = 0 on the first iteration)
+//   Hp = Kp + W p ; alpha = rz / p.Hp ; delta += alpha p ; r -= alpha Hp ; converged when |r| <= eta |b|
 template <int Q>
-__global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict__ p, const double *__restrict__ Kp,
+__global__ void __launch_bounds__(256) pcg_step_kernel(double *__restrict__ p, double *__restrict__ Kp,
                                                        const double *__restrict__ W, double *__restrict__ Hp,
                                                        double *__restrict__ delta, double *__restrict__ r,
                                                        const int *act, int T, double *__restrict__ pcg_s,
-                                                       int *__restrict__ conv, const int *__restrict__ cnt, CgTail tail) {
+                                                       int *__restrict__ conv, const int *__restrict__ cnt, CgTail tail,
+                                                       const double *__restrict__ z, int first) {
     __shared__ double red[32];
     __shared__ int s_last, s_wsum[8], s_running;
     const int n_act = cnt ? *cnt : (int)gridDim.x;
@@ -533,6 +523,16 @@ __global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict_
     const bool zero_rhs = pcg_s[trial * 4 + 1] == 0.0;   // zero gradient: delta = 0 is exact (pcg_init flagged it converged)
     if (zero_rhs && threadIdx.x == 0) conv[trial] = 1;
     if (!zero_rhs) {
+    double rz = 0.0;
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) rz += r[base + i] * z[base + i];
+    rz = block_sum(rz, red);
+    const double beta = first ? 0.0 : rz / pcg_s[trial * 4 + 0];
+    for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
+        p[base + i] = z[base + i] + (first ? 0.0 : beta * p[base + i]);
+        Kp[base + i] = Hp[base + i] + (first ? 0.0 : beta * Kp[base + i]);       // Hp's buffer holds Nr on entry
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) pcg_s[trial * 4 + 0] = rz;
     double pHp = 0.0;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         double pk[Q], hv[Q];
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) pcg_step_kernel(const double *__restrict_
         }
     }
     pHp = block_sum(pHp, red);
-    const double alpha = pcg_s[trial * 4 + 0] / pHp;
+    const double alpha = rz / pHp;
     double rr = 0.0;
     for (int i = threadIdx.x; i < Q * T; i += blockDim.x) {
         delta[base + i] += alpha * p[base + i];
@@ -611,16 +611,10 @@ int launch_pcg_init(const double *g, double *r, double *delta, const int *act, i
     return PGPFA_OK;
 }
 template <int Q>
-int launch_pcg_dir(const double *r, const double *z, double *p, const int *act, int nslots, int T, int first, double *pcg_s,
-                   cudaStream_t st, const int *cnt) {
-    pcg_dir_kernel<Q><<<nslots, 256, 0, st>>>(r, z, p, act, T, first, pcg_s, cnt);
-    PGPFA_LAUNCH_CHECK();
-    return PGPFA_OK;
-}
-template <int Q>
-int launch_pcg_step(const double *p, const double *Kp, const double *W, double *Hp, double *delta, double *r, const int *act,
-                    int nslots, int T, double *pcg_s, int *conv, cudaStream_t st, const int *cnt, CgTail tail) {
-    pcg_step_kernel<Q><<<nslots, 256, 0, st>>>(p, Kp, W, Hp, delta, r, act, T, pcg_s, conv, cnt, tail);
+int launch_pcg_step(double *p, double *Kp, const double *W, double *Hp, double *delta, double *r, const int *act,
+                    int nslots, int T, double *pcg_s, int *conv, cudaStream_t st, const int *cnt, CgTail tail, const double *z,
+                    int first) {
+    pcg_step_kernel<Q><<<nslots, 256, 0, st>>>(p, Kp, W, Hp, delta, r, act, T, pcg_s, conv, cnt, tail, z, first);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -678,10 +672,10 @@ int launch_linesearch(double *x, const double *dx, const double *Kx, const doubl
 }  // namespace
 
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
-                        cudaStream_t st, const int *cnt) {
+                        cudaStream_t st, const int *cnt, double *out2) {
     if (nslots <= 0) return PGPFA_OK;
-    dim3 grid(q, (T + PA_TS - 1) / PA_TS, (nslots + PA_TN - 1) / PA_TN);
-    prior_apply_kernel<<<grid, 128, 0, st>>>(Kmat, v, out, act, nslots, q, T, cnt);
+    dim3 grid(out2 ? 2 * q : q, (T + PA_TS - 1) / PA_TS, (nslots + PA_TN - 1) / PA_TN);
+    prior_apply_kernel<<<grid, 128, 0, st>>>(Kmat, v, out, act, nslots, q, T, cnt, out2);
     PGPFA_LAUNCH_CHECK();
     return PGPFA_OK;
 }
@@ -794,7 +788,7 @@ size_t lap_fixed_bytes(int R, int q, int T, int npairs_max) {
     b += align_up((size_t)R * q * q * T * 8);
     b += 2 * align_up((size_t)R * 8);
     b += 5 * align_up((size_t)R * 4) + 256;
-    b += 2 * align_up((size_t)q * T * T * 8) + 2 * align_up((size_t)q * 8) + align_up((size_t)q * WD_PARTS * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
+    b += align_up((size_t)q * T * T * 8) + align_up((size_t)2 * q * T * T * 8) + 2 * align_up((size_t)q * 8) + align_up((size_t)q * WD_PARTS * 8) + align_up((size_t)pgpfa_spd_inverse_workspace_bytes(q, T));
     b += align_up((size_t)npairs_max * sizeof(int2)) + align_up(PGPFA_LOWRANK_TABLE_BYTES);
     b += align_up(pgpfa_i_pautosum_partial_bytes(q, T));
     return b;
@@ -844,7 +838,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     w.pairs = (int2 *)take((size_t)ltl * sizeof(int2));
     w.lr_tables = take(PGPFA_LOWRANK_TABLE_BYTES);
     w.pauto_partial = (double *)take(pgpfa_i_pautosum_partial_bytes(q, T));
-    w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)q * T * T * 8);
+    w.Mk = (double *)take((size_t)q * T * T * 8); w.Minv = (double *)take((size_t)2 * q * T * T * 8);
     w.wbar = (double *)take((size_t)q * WD_PARTS * 8); w.plogdet = (double *)take((size_t)q * 8); w.pinfo = (int *)take((size_t)q * 8);
     w.pws_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
     w.pws = take((size_t)w.pws_bytes);
@@ -931,6 +925,11 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                     shift_diag_kernel<<<gsh, 256, 0, st>>>(Kinv, w.wbar, 1.0 / ((double)cn * T), T, w.Mk);
                     PGPFA_LAUNCH_CHECK();
                     PGPFA_TRY(pgpfa_spd_inverse_batched(w.Mk, q, T, w.Minv, w.plogdet, w.pinfo, w.pws, w.pws_bytes, st));
+                    // N_k = K_k^-1 M_k^-1 behind the q inverses (both symmetric functions of K_k: N_k[j][s] =
+                    // sum_t Kinv_k[s][t] Minv_k[j][t] is prior_apply with the T rows of Minv_k as "trials", q = 1)
+                    for (int k = 0; k < q; k++)
+                        PGPFA_TRY(pgpfa_i_prior_apply(Kinv + (size_t)k * T * T, w.Minv + (size_t)k * T * T,
+                                                      w.Minv + (size_t)(q + k) * T * T, nullptr, T, 1, T, st));
                     pgpfa_prof_end(h, st);
                 }
                 // PCG over the trials of this Newton iteration; converged trials drop out of `cg`
@@ -955,15 +954,15 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                         if (c < ub_cg) ub_cg = c;
                     }
                     pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
-                    PGPFA_TRY(pgpfa_i_prior_apply(w.Minv, w.pr, w.pz, cg, ub_cg, q, T, st, cnt_cg));
-                    PCG_DISPATCH(launch_pcg_dir, w.pr, w.pz, w.pp, cg, ub_cg, T, ci == 0, w.pcg_s, st, cnt_cg)
-                    PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.pp, w.Kd, cg, ub_cg, q, T, st, cnt_cg));
+                    // z = M^-1 r -> pz and K^-1 M^-1 r -> pHp in one launch (matrices stacked in w.Minv)
+                    PGPFA_TRY(pgpfa_i_prior_apply(w.Minv, w.pr, w.pz, cg, ub_cg, q, T, st, cnt_cg, w.pHp));
                     unsigned long long sq;
                     int *word;
                     PGPFA_TRY(pgpfa_prog_alloc(h, &sq, &word));
                     CgTail tail;
                     tail.ticket = w.cnt + 16; tail.list_out = cg_next; tail.cnt_out = cnt_cg_next; tail.prog = word;
-                    PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, ub_cg, T, w.pcg_s, w.conv, st, cnt_cg, tail)
+                    PCG_DISPATCH(launch_pcg_step, w.pp, w.Kd, w.W, w.pHp, w.dx, w.pr, cg, ub_cg, T, w.pcg_s, w.conv, st, cnt_cg, tail,
+                                 w.pz, ci == 0)
                     pgpfa_prof_end(h, st);
                     cg_seq.push_back(sq);
                     cg_seq_all.push_back(sq);
