@@ -860,7 +860,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
     if (use_lr) PGPFA_TRY(pgpfa_i_lowrank_prepare(h, *lr, q, T, w.lr_tables, st));
     if (pautosum && !use_lr && !vsmGP) return PGPFA_ERR_ARG;     // the dense path sums the per-trial blocks it is given
     const int npairs = pgpfa_i_num_pairs(q, T, cov_dense != nullptr);
-    PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, cov_dense != nullptr, st));
+    bool pairs_ready = false;          // the tile-pair table of the selected inverse: generated only if the dense pass runs
 
     PgpfaMatSrc ms;
     ms.Kinv = Kinv; ms.W = w.W; ms.dense = nullptr; ms.q = q; ms.T = T; ms.n = n; ms.diag_scale = 1.0;
@@ -1103,6 +1103,10 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             pgpfa_prof_begin(h, PGPFA_PROF_SLICES, st);
             if (vsm) PGPFA_TRY(pgpfa_i_timediag(w.ZT, w.actA, vsm, n, q, T, cn, st));
             PGPFA_CUDA_TRY(cudaEventRecord(h->ev_means, st));      // pgpfa_stream_wait_means
+            if ((vsmGP || cov_dense) && !pairs_ready) {
+                PGPFA_TRY(pgpfa_i_gen_pairs(w.pairs, q, T, cov_dense != nullptr, st));
+                pairs_ready = true;
+            }
             if (vsmGP || cov_dense)
                 PGPFA_TRY(pgpfa_i_lauum(w.ZT, w.pairs, npairs, w.actA, vsmGP,
                                         cov_dense ? cov_dense + (size_t)c0 * n * n : nullptr, n, q, T, cn, st));
