@@ -46,6 +46,16 @@ def read_packed(tensors):
     return out
 
 
+_PRIOR_SIDE = {}
+
+
+def _prior_side_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _PRIOR_SIDE:
+        _PRIOR_SIDE[dev] = torch.cuda.Stream(device=dev)
+    return _PRIOR_SIDE[dev]
+
+
 class DeviceParams:
     """C (N,q), d (N), tau (q, seconds) on the device plus the derived prior blocks.
 
@@ -72,9 +82,22 @@ class DeviceParams:
     def prepare(self):
         if self._K is None:
             self._K = kn.make_K(self.tau, self.T, self.binSize, EPS_NOISE)
+            if self._use_lr:
+                # the pivoted Cholesky (one CTA per latent, ~0.12 ms of pure latency) runs on a side stream beside the
+                # inverse of K (one CTA per latent as well); both only read K, and the caller's stream waits for both
+                q, T = self.q, self.T
+                out = (kn.empty(q, T, T), kn.empty(q, T, T), kn.empty(q, dtype=torch.int32))
+                main, side = torch.cuda.current_stream(), _prior_side_stream()
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self._lr_dev = kn.prior_lowrank_async(self._K, EPS_NOISE, LOWRANK_DELTA, out=out)
+                    ev_lr = torch.cuda.Event()
+                    ev_lr.record(side)
             self._Kinv, self._logdetK, self._Kinfo = kn.spd_inverse(self._K)
             if self._use_lr:
-                self._lr_dev = kn.prior_lowrank_async(self._K, EPS_NOISE, LOWRANK_DELTA)
+                torch.cuda.current_stream().wait_event(ev_lr)
         return self
 
     def pending(self):

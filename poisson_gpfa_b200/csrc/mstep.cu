@@ -278,12 +278,21 @@ __global__ void mstep_cd_update_kernel(const double *__restrict__ stats, double 
 // 4 warps as 2x2 of 32x32, k in chunks of 16 through double-buffered padded shared memory (conflict-free fragment
 // loads: A stride 20 and B stride 68 doubles put the 16 lanes of a half-warp on 16 distinct 8-byte banks); the next
 // chunk's global loads are in flight while the current one is multiplied.
+// Two problem sets in one launch (grid.z = 2 nb): batch b < nb is C[b] = A[b] B[b]; batch nb + b is
+// C2[b] = A2[b % qmod] A[b] (the timescale gradient needs K^-1 dK and P K^-1: independent products, one launch).
 __global__ void __launch_bounds__(128) small_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
-                                                         double *__restrict__ Cm, int n) {
+                                                         double *__restrict__ Cm, int n, const double *__restrict__ A2,
+                                                         double *__restrict__ C2, int nb, int qmod) {
     __shared__ double As[2][64][20], Bs[2][16][68];
     const int b = blockIdx.z;
-    const double *Ab = A + (size_t)b * n * n, *Bb = B + (size_t)b * n * n;
-    double *Cb = Cm + (size_t)b * n * n;
+    const double *Ab, *Bb;
+    double *Cb;
+    if (b < nb) {
+        Ab = A + (size_t)b * n * n; Bb = B + (size_t)b * n * n; Cb = Cm + (size_t)b * n * n;
+    } else {
+        const int b2 = b - nb;
+        Ab = A2 + (size_t)(b2 % qmod) * n * n; Bb = A + (size_t)b2 * n * n; Cb = C2 + (size_t)b2 * n * n;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     const int fr = lane >> 2, fk = lane & 3;
@@ -336,9 +345,11 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const double *__restric
 // cost / gradient of the timescale objective from Kinv, logdet, dK, G = Kinv dK Kinv and PautoSum.
 // Stage 1: TAU_PARTS CTAs per slot reduce slices of the three traces; stage 2 adds them in a fixed order.
 #define TAU_PARTS 8
+// G = P K^-1 and M1 = K^-1 dK (small_gemm_kernel): t3 = tr(K^-1 dK K^-1 P) = sum_e M1[e] G[e]
 __global__ void __launch_bounds__(256) tau_trace_kernel(const double *__restrict__ Kinv, const double *__restrict__ dK,
                                                         const double *__restrict__ G, const double *__restrict__ P, int T,
-                                                        double *__restrict__ part, int qmod) {
+                                                        double *__restrict__ part, int qmod,
+                                                        const double *__restrict__ M1) {
     __shared__ double red[32];
     const int k = blockIdx.x;
     const size_t off = (size_t)k * T * T, poff = (size_t)(k % qmod) * T * T;
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(256) tau_trace_kernel(const double *__restrict
         const double ki = Kinv[off + e], pp = P[poff + e];
         t1 += ki * pp;
         t2 += ki * dK[off + e];
-        t3 += G[off + e] * pp;
+        t3 += G[off + e] * M1[off + e];
     }
     t1 = block_sum(t1, red);
     t2 = block_sum(t2, red);
@@ -492,13 +503,12 @@ static int tau_eval_impl(const double *p, const double *Psum, double numTrials, 
     const long long inv_bytes = pgpfa_spd_inverse_workspace_bytes(q, T);
     PGPFA_TRY(pgpfa_make_K_gamma(p, q, T, eps, K, dK, st));
     PGPFA_TRY(pgpfa_spd_inverse_batched(K, q, T, Kinv, logdet, info, w, inv_bytes, st));
-    dim3 grid((T + 63) / 64, (T + 63) / 64, q);
-    small_gemm_kernel<<<grid, 128, 0, st>>>(Kinv, dK, M1, T);
-    PGPFA_LAUNCH_CHECK();
-    small_gemm_kernel<<<grid, 128, 0, st>>>(M1, Kinv, G, T);
+    // tr(K^-1 dK K^-1 P) = sum_ij (K^-1 dK)_ij (P K^-1)_ij: the two products are independent, one launch
+    dim3 grid((T + 63) / 64, (T + 63) / 64, 2 * q);
+    small_gemm_kernel<<<grid, 128, 0, st>>>(Kinv, dK, M1, T, Psum, G, q, qmod);
     PGPFA_LAUNCH_CHECK();
     dim3 gtr(q, TAU_PARTS);
-    tau_trace_kernel<<<gtr, 256, 0, st>>>(Kinv, dK, G, Psum, T, part, qmod);
+    tau_trace_kernel<<<gtr, 256, 0, st>>>(Kinv, dK, G, Psum, T, part, qmod, M1);
     PGPFA_LAUNCH_CHECK();
     tau_reduce_kernel<<<(q + 127) / 128, 128, 0, st>>>(p, part, logdet, q, numTrials, prior_w, tau_old, bs, cost, grad, qmod);
     PGPFA_LAUNCH_CHECK();

@@ -178,11 +178,13 @@ class LaplaceResult:
     __slots__ = ("x", "f", "vsm", "vsmGP", "cov", "niter", "info", "stats", "rc", "pautosum")
 
 
-def prior_lowrank_async(K, eps=0.001, delta=1e-14):
-    """Pivoted Cholesky K_k - eps I = F_k F_k^T (pgpfa_prior_lowrank), enqueued only: (F, Ft, ranks as a DEVICE tensor)."""
+def prior_lowrank_async(K, eps=0.001, delta=1e-14, out=None):
+    """Pivoted Cholesky K_k - eps I = F_k F_k^T (pgpfa_prior_lowrank), enqueued only: (F, Ft, ranks as a DEVICE tensor).
+    `out` = preallocated (F, Ft, rank) when the call is made under another stream than the one that owns the memory."""
     q, T, _ = K.shape
-    F, Ft = empty(q, T, T), empty(q, T, T)
-    rank = empty(q, dtype=torch.int32)
+    if out is None:
+        out = (empty(q, T, T), empty(q, T, T), empty(q, dtype=torch.int32))
+    F, Ft, rank = out
     call("pgpfa_prior_lowrank", ptr(K), q, T, float(eps), float(delta), ptr(F), ptr(Ft), ptr(rank), stream())
     return F, Ft, rank
 
