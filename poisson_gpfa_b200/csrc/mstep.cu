@@ -484,6 +484,15 @@ extern "C" long long pgpfa_tau_eval_workspace_bytes(int q, int T) {
            pgpfa_spd_inverse_workspace_bytes(q, T) + 1024;
 }
 
+// C[b] = A[b] B[b] for `batch` n x n matrices on DMMA (internal: the CG preconditioner's N_k = K_k^-1 M_k^-1)
+int pgpfa_i_small_gemm(const double *A, const double *B, double *C, int n, int batch, cudaStream_t st) {
+    if (batch <= 0 || n <= 0) return PGPFA_OK;
+    dim3 grid((n + 63) / 64, (n + 63) / 64, batch);
+    small_gemm_kernel<<<grid, 128, 0, st>>>(A, B, C, n, nullptr, nullptr, batch, 1);
+    PGPFA_LAUNCH_CHECK();
+    return PGPFA_OK;
+}
+
 static int tau_eval_impl(const double *p, const double *Psum, double numTrials, int q, int qmod, int T, double eps,
                          double prior_w, const double *tau_old, double bs, double *cost, double *grad, void *workspace,
                          long long ws_bytes, cudaStream_t st) {

@@ -90,6 +90,7 @@ struct LooMap { const int *ymap; const int *excl; };
 static inline LooMap pgpfa_no_loo() { LooMap l; l.ymap = nullptr; l.excl = nullptr; return l; }
 
 // `cnt` (optional, device): the true number of slots; nslots is then only the host's upper bound that sizes the grid
+int pgpfa_i_small_gemm(const double *A, const double *B, double *C, int n, int batch, cudaStream_t st);   // mstep.cu
 // `out2` (optional): Kmat holds 2 q matrices; matrices q .. 2q-1 are applied to the same vectors and land in out2
 int pgpfa_i_prior_apply(const double *Kmat, const double *v, double *out, const int *act, int nslots, int q, int T,
                         cudaStream_t st, const int *cnt = nullptr, double *out2 = nullptr);
