@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
             const double eta = pcg_s[trial * 4 + 2];
             const double rel = sl / scale;
             state = (0.2 * rel * rel + 2.0 * eta * rel <= 0.1 * tol || rel <= 0.01 * tol) ? 1 : 0;
-            if (state == 0 && (alpha < 0.01 || step_kind >= 2000 + 14)) state = 2;   // struggling: hand over to exact Newton
+            if (state == 0 && (alpha < 0.01 || step_kind % 100000 >= 2000 + 14)) state = 2;   // struggling: hand over to exact Newton
             // Forcing term of the next solve.  Default 0.03 * (relative step just taken): superlinear overall.  When the
             // NEXT step can be the last one (its quadratic term alone is below the aim of 0.002 tol, 50x under the exit
             // threshold), eta is set to what makes it the last one under the exit test's own model
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) laplace_linesearch_kernel(
             const double e_pred = 0.2 * rel * rel + 2.0 * eta * rel;
             const double aim = 0.002 * tol;
             double eta_next = 0.03 * rel;
-            if (0.2 * e_pred * e_pred < 0.5 * aim) eta_next = (aim - 0.2 * e_pred * e_pred) / (2.0 * e_pred);
+            if (step_kind < 100000 && 0.2 * e_pred * e_pred < 0.5 * aim) eta_next = (aim - 0.2 * e_pred * e_pred) / (2.0 * e_pred);
             pcg_s[trial * 4 + 2] = fmin(1e-2, fmax(1e-9, eta_next));
         } else {
             const double rho = (prev > 0.0) ? sl / prev : 1.0;
@@ -906,6 +906,8 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
             // the host-driven loop (every count is awaited before the next iteration is enqueued): the iterates are
             // bit-identical for every depth.
             const int depth = h->loop_depth;
+            // PGPFA_FORCING=0 (development switch): plain 0.03 * rel forcing terms, no finish-next rule
+            static const int forcing_off = [] { const char *e = getenv("PGPFA_FORCING"); return (e && atoi(e) == 0) ? 100000 : 0; }();
             int *cnt_act = w.cnt + 0, *cnt_act_next = w.cnt + 1, *cnt_cg = w.cnt + 2, *cnt_cg_next = w.cnt + 3;
             set_count_kernel<<<1, 1, 0, st>>>(cnt_act, cn);
             PGPFA_LAUNCH_CHECK();
@@ -982,7 +984,7 @@ static int laplace_solve_impl(pgpfa_handle_t h, const double *y, const double *C
                 pgpfa_prof_begin(h, PGPFA_PROF_EVAL, st);
                 PGPFA_TRY(pgpfa_i_prior_apply(Kinv, w.dx, w.Kd, act, ub_act, q, T, st, cnt_act));
                 PGPFA_TRY(pgpfa_i_linesearch(x, w.dx, w.Kx, w.Kd, w.g, y, C, d, act, ub_act, q, N, T, tol, w.fcur, w.conv,
-                                             niter, w.steplen, 2000 + it, st, nullptr, loo, w.pcg_s, cnt_act));
+                                             niter, w.steplen, 2000 + it + forcing_off, st, nullptr, loo, w.pcg_s, cnt_act));
                 pgpfa_prof_end(h, st);
                 int *outp = (act == w.actA) ? w.actB : w.actA;
                 unsigned long long sq;
