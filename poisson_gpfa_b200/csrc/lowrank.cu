@@ -14,8 +14,13 @@
 // instead of 3.2 GFLOP.  The dense tiled path stays for priors whose numerical rank is not small (short timescales)
 // and for the dense covariance output.
 //
-// All GEMM-shaped steps (F^T Dt F, F L_b^-T, Y_k Y_k^T) run through one batched NT kernel on the FP64 tensor pipe
-// (DMMA.8x8x4); the r x r factorisation and triangular inverse are the tile kernels of factor.cu.
+// The GEMM-shaped steps run on the FP64 tensor pipe (DMMA.8x8x4): F^T Dt F as ONE product per latent pair over all
+// slots against a feature matrix (cap_features_kernel + gemm_nt_kernel with the scatter epilogue), F L_b^-T through the
+// batched NT kernel (only the columns the triangular factor makes non-zero), the per-bin mixing and the per-bin slices
+// as one-warp-per-bin DMMA sweeps over Y, and — what the timescale M-step actually consumes — the TRIAL-SUM of
+// eps diag(P) + Y_k Y_k^T + m_k m_k^T (PautoSum, funs/learning.py:162-165) by the tile-pair SYRK kernels, so the per-trial
+// T x T blocks are only written when a caller asks for post_vsmGP.  The r x r factorisation and triangular inverse are
+// the tile kernels of factor.cu.
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
