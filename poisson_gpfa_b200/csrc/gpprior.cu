@@ -146,8 +146,11 @@ namespace {
 //     d = A_kk;  A_ij -= A_ik A_kj / d;  A_ik = A_ik / d;  A_kk = -1 / d        (k = 0 .. n-1  ->  -A^-1)
 // whose pivots are those of the Cholesky / LDL^T factorisation (logdet = sum log d).  Per step the column k goes
 // through shared memory (double-buffered: one __syncthreads per step) and every thread does SW_TS^2 DFMAs on registers; row
-// and column k are folded into the same rank-1 form (u_k = 1 - 1/d, w_k = d - 1, then A_kk -= 2) so there is no
-// per-element select.
+// and column k are folded into the same rank-1 form (u_k = 1 - 1/d, w_k = d - 1; A_kk = -1/d is then set by its owner) so
+// there is no per-element select.  The folded entries c_i - (c_i / d)(d - 1) = c_i / d carry a relative rounding error of
+// ~eps * max(1, d): nothing for the unit-diagonal prior blocks this is used on (every pivot <= 1), ~1e-13 for pivots of
+// 1e3 (tests/test_sweep_algebra.py shows the effect and the Jacobi equilibration that removes it; in this kernel the
+// equilibration costs more registers than it has: +13 % run time, so it is left to callers with badly scaled input).
 // ---------------------------------------------------------------------------------------------
 #define SW_TS 10                       // tile edge: 100 doubles of the matrix per thread
 #define SW_THREADS 256                 // 2 warps per SM sub-partition -> 255 registers per thread
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) spd_sweep_kernel(const double *
         tj = t - ti * (ti + 1) / 2;
     }
     const double *Ab = A + (size_t)blockIdx.x * n * n;
+    if (t == 0) s_bad = 0;
     double a[TS][TS];
 #pragma unroll
     for (int r = 0; r < TS; r++)
@@ -179,7 +183,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) spd_sweep_kernel(const double *
             const int i = ti * TS + r, j = tj * TS + c;
             a[r][c] = (live && i < n && j < n) ? Ab[(size_t)i * n + j] : (i == j ? 1.0 : 0.0);   // identity padding
         }
-    if (t == 0) s_bad = 0;
     if (live && tj == 0) {
 #pragma unroll
         for (int r = 0; r < TS; r++) cbuf[0][ti * TS + r] = a[r][0];
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) spd_sweep_kernel(const double *
                     for (int c = 0; c < TS; c++)
                         if (c != kn) a[r][c] = fma(-u, w[c], a[r][c]);
                 }
-                if (rowk && tj == tk) a[kk][kk] -= 2.0;
+                if (rowk && tj == tk) a[kk][kk] = -dinv;            // exact (the folded form would cancel d - (d - 2 + 1/d))
             }
             __syncthreads();
         }

@@ -60,6 +60,30 @@ def test_spd_inverse(n, b):
     assert rel(logdet, np.linalg.slogdet(A)[1]) <= 1e-13
 
 
+@pytest.mark.parametrize("n,b", [(1, 2), (7, 3), (10, 1), (11, 4), (199, 2), (208, 72), (220, 3), (221, 2)])
+def test_spd_inverse_register_resident_sweep_and_its_limits(n, b):
+    """n <= 220 goes through the one-CTA-per-matrix sweep (gpprior.cu: spd_sweep_kernel; 10 x 10 register tiles, ragged
+    last tile padded with the identity), n = 221 through the tile-kernel chain: same results, symmetric output."""
+    from poisson_gpfa_b200 import kernels as kn
+    rng = np.random.RandomState(1000 + n)
+    A = random_spd(rng, b, n)
+    Ainv, logdet, info = kn.spd_inverse(dev(A))
+    assert int(info.abs().max()) == 0
+    assert rel(Ainv, np.linalg.inv(A)) <= 1e-11
+    ld = np.linalg.slogdet(A)[1]
+    assert np.abs(logdet.cpu().numpy() - ld).max() <= 1e-12 * max(1.0, np.abs(ld).max())
+    assert torch.equal(Ainv, Ainv.transpose(1, 2))
+
+
+def test_spd_inverse_reports_the_first_non_positive_pivot():
+    from poisson_gpfa_b200 import kernels as kn
+    rng = np.random.RandomState(5)
+    A = random_spd(rng, 3, 40)
+    A[1, 7, 7] = -1.0                     # the 8th pivot of matrix 1 is negative
+    _, _, info = kn.spd_inverse(dev(A))
+    assert info.cpu().numpy().tolist() == [0, 8, 0]
+
+
 def test_kinv_of_prior():
     from poisson_gpfa_b200 import kernels as kn
     tau = np.linspace(0.05, 0.3, 8)
