@@ -291,6 +291,11 @@ def run_ours(args):
     launches0 = _lib.lib.pgpfa_launch_count()
     syncs0, thr0 = _lib.host_sync_count(), _lib.lib.pgpfa_throttle_wait_count(h)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # no garbage-collector pause inside the timed region (a full collection over the torch objects of the warm-up can
+    # take tens of ms: several steps' worth at 8 GPUs)
+    import gc
+    gc.collect()
+    gc.disable()
     barrier()
     sampler.begin()
     e0.record()
@@ -309,6 +314,7 @@ def run_ours(args):
     e1.record()
     barrier()
     sampler.end()
+    gc.enable()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.lib.pgpfa_launch_count() - launches0
