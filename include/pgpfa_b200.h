@@ -75,7 +75,9 @@ int pgpfa_make_K(const double *tau_sec, int q, int T, double binSize_ms, double 
 int pgpfa_make_K_big(const double *K, int q, int T, double *K_big, cudaStream_t stream);
 /* K(p), dK/dgamma for the timescale M-step, gamma = exp(p) in bins^-2: funs/learning.py:183-185 */
 int pgpfa_make_K_gamma(const double *p, int q, int T, double epsNoise, double *K, double *dK, cudaStream_t stream);
-/* batched SPD inverse + logdet through the tiled Cholesky (np.linalg.inv / slogdet replacement) */
+/* batched SPD inverse + logdet (np.linalg.inv / slogdet replacement, funs/inference.py:82, funs/learning.py:186-192):
+ * n <= 220 one register-resident CTA per matrix (symmetric sweep, pivots of LDL^T), larger n the tiled Cholesky chain.
+ * info[b] = 0, or 1 + the index of the first non-positive pivot.  Ainv must not alias A. */
 long long pgpfa_spd_inverse_workspace_bytes(int batch, int n);
 int pgpfa_spd_inverse_batched(const double *A, int batch, int n, double *Ainv, double *logdet, int *info,
                               void *workspace, long long ws_bytes, cudaStream_t stream);
